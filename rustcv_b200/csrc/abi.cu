@@ -1,0 +1,600 @@
+// abi.cu -- the extern "C" entry points declared in include/rcv_imgproc.h.
+//
+// Everything here is host plumbing: argument validation (the reference's loops
+// silently return on short buffers, rustcv/src/videoio/mod.rs:346-348; this ABI returns
+// a code instead), staging of host-resident Mats through device scratch, batching, and
+// the synchronous-by-default contract of the reference API (README.md:31).
+#include "rcv_internal.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace rcv;
+
+namespace {
+
+size_t elem_size(int depth) { return depth == RCV_F32 ? 4 : 1; }
+size_t mat_row_bytes(const RcvMat *m) { return (size_t)m->cols * m->channels * elem_size(m->depth); }
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+bool is_host(const RcvMat *m) { return m->loc != RCV_DEVICE; }
+
+int check_mat(const RcvMat *m, const char *name) {
+  if (!m) return fail(RCV_ERR_ARG, "%s is NULL", name);
+  if (m->rows < 0 || m->cols < 0) return fail(RCV_ERR_ARG, "%s has negative dimensions", name);
+  if (m->channels < 1 || m->channels > 4) return fail(RCV_ERR_DEPTH, "%s.channels = %d (want 1..4)", name, m->channels);
+  if (m->depth != RCV_U8 && m->depth != RCV_F32) return fail(RCV_ERR_DEPTH, "%s.depth = %d", name, m->depth);
+  if (m->loc > RCV_HOST_PINNED) return fail(RCV_ERR_ARG, "%s.loc = %d", name, m->loc);
+  if (m->rows > 0 && m->cols > 0) {
+    if (!m->data) return fail(RCV_ERR_ARG, "%s.data is NULL", name);
+    if (m->step < mat_row_bytes(m))
+      return fail(RCV_ERR_SIZE, "%s.step %zu < row bytes %zu", name, m->step, mat_row_bytes(m));
+    if (m->depth == RCV_F32 && ((m->step & 3) || ((uintptr_t)m->data & 3)))
+      return fail(RCV_ERR_SIZE, "%s: f32 data/step must be 4-byte aligned", name);
+  }
+  return RCV_OK;
+}
+
+int check_same_size(const RcvMat *a, const RcvMat *b, const char *what) {
+  if (a->rows != b->rows || a->cols != b->cols)
+    return fail(RCV_ERR_SIZE, "%s: dst is %dx%d, expected %dx%d (the caller sizes dst)", what, b->rows, b->cols, a->rows,
+                a->cols);
+  return RCV_OK;
+}
+
+DView view_of(const RcvMat *m, void *data, size_t step) {
+  DView v;
+  v.data = (uint8_t *)data;
+  v.rows = m->rows;
+  v.cols = m->cols;
+  v.step = step;
+  v.cn = m->channels;
+  v.depth = m->depth;
+  return v;
+}
+
+DBatch single(const DView &v) {
+  DBatch b;
+  b.v = v;
+  b.frame_stride = 0;
+  b.n = 1;
+  return b;
+}
+
+DBatch none_batch() {
+  DBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = 1;
+  return b;
+}
+
+// the context an op runs on: the device of any device-resident Mat, else the default
+Ctx *pick_ctx(const RcvMat *const *mats, int n) {
+  int dev = -1;
+  for (int i = 0; i < n; ++i) {
+    if (!mats[i] || mats[i]->loc != RCV_DEVICE) continue;
+    if (dev >= 0 && mats[i]->device != dev) {
+      set_error("Mats live on different GPUs (%d and %d)", dev, mats[i]->device);
+      return nullptr;
+    }
+    dev = mats[i]->device;
+  }
+  return dev >= 0 ? ctx_get(dev) : ctx_default();
+}
+
+// A Mat made usable by a kernel: device Mats are used in place, host Mats get device
+// scratch with a 256-byte aligned pitch.
+struct Staged {
+  DView v;
+  bool staged = false;
+};
+
+int stage_alloc(Ctx *c, const RcvMat *m, int slot, Staged *out) {
+  if (!is_host(m)) {
+    out->v = view_of(m, m->data, m->step);
+    out->staged = false;
+    return RCV_OK;
+  }
+  size_t pitch = align_up(mat_row_bytes(m), 256);
+  if (pitch == 0) pitch = 256;
+  void *p = nullptr;
+  RCV_TRY(ctx_scratch(c, slot, pitch * (size_t)(m->rows > 0 ? m->rows : 1), &p));
+  out->v = view_of(m, p, pitch);
+  out->staged = true;
+  return RCV_OK;
+}
+
+int copy_in(const RcvMat *m, const Staged &st, cudaStream_t s) {
+  if (!st.staged || m->rows == 0 || m->cols == 0) return RCV_OK;
+  RCV_CUDA(cudaMemcpy2DAsync(st.v.data, st.v.step, m->data, m->step, mat_row_bytes(m), m->rows,
+                             cudaMemcpyHostToDevice, s));
+  return RCV_OK;
+}
+
+int copy_out(const RcvMat *m, const Staged &st, cudaStream_t s) {
+  if (!st.staged || m->rows == 0 || m->cols == 0) return RCV_OK;
+  RCV_CUDA(cudaMemcpy2DAsync(m->data, m->step, st.v.data, st.v.step, mat_row_bytes(m), m->rows,
+                             cudaMemcpyDeviceToHost, s));
+  return RCV_OK;
+}
+
+// Runs `launch(ctx, src_batch, dst_batch, stream)` for one src -> one dst.
+template <class F>
+int run_unary(const RcvMat *src, RcvMat *dst, F launch) {
+  const RcvMat *mats[2] = {src, dst};
+  Ctx *c = pick_ctx(mats, 2);
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Staged si, so;
+  RCV_TRY(stage_alloc(c, src, SCR_STAGE_IN0, &si));
+  RCV_TRY(stage_alloc(c, dst, SCR_STAGE_OUT0, &so));
+  RCV_TRY(copy_in(src, si, c->stream));
+  RCV_TRY(launch(c, single(si.v), single(so.v), c->stream));
+  RCV_TRY(copy_out(dst, so, c->stream));
+  if (ctx_blocking() || si.staged || so.staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
+  return RCV_OK;
+}
+
+// Batches.  Device Mats with a uniform frame stride: one launch.  Device Mats otherwise:
+// one launch per frame.  Host Mats: H2D / kernel / D2H pipelined over a ring of kRing slots.
+bool uniform_device_batch(const RcvMat *m, int n, DBatch *out) {
+  for (int i = 0; i < n; ++i)
+    if (m[i].loc != RCV_DEVICE || m[i].device != m[0].device) return false;
+  ptrdiff_t stride = n > 1 ? (uint8_t *)m[1].data - (uint8_t *)m[0].data : 0;
+  if (n > 1 && stride <= 0) return false;
+  for (int i = 1; i < n; ++i)
+    if ((uint8_t *)m[i].data - (uint8_t *)m[i - 1].data != stride) return false;
+  out->v = view_of(&m[0], m[0].data, m[0].step);
+  out->frame_stride = (size_t)stride;
+  out->n = n;
+  return true;
+}
+
+int check_batch_geometry(const RcvMat *m, int n, const char *name) {
+  for (int i = 0; i < n; ++i) {
+    RCV_TRY(check_mat(&m[i], name));
+    if (m[i].rows != m[0].rows || m[i].cols != m[0].cols || m[i].channels != m[0].channels ||
+        m[i].depth != m[0].depth || m[i].step != m[0].step || m[i].loc != m[0].loc)
+      return fail(RCV_ERR_SIZE, "%s[%d] differs in geometry/location from %s[0]", name, i, name);
+  }
+  return RCV_OK;
+}
+
+template <class F>
+int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch) {
+  if (n == 0) return RCV_OK;
+  std::vector<const RcvMat *> mats;
+  for (int i = 0; i < n; ++i) {
+    mats.push_back(&srcs[i]);
+    mats.push_back(&dsts[i]);
+  }
+  Ctx *c = pick_ctx(mats.data(), (int)mats.size());
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const bool src_host = is_host(&srcs[0]), dst_host = is_host(&dsts[0]);
+  if (!src_host && !dst_host) {
+    DBatch sb, db;
+    if (uniform_device_batch(srcs, n, &sb) && uniform_device_batch(dsts, n, &db)) {
+      RCV_TRY(launch(c, sb, db, c->stream));
+    } else {
+      for (int i = 0; i < n; ++i)
+        RCV_TRY(launch(c, single(view_of(&srcs[i], srcs[i].data, srcs[i].step)),
+                       single(view_of(&dsts[i], dsts[i].data, dsts[i].step)), c->stream));
+    }
+    if (ctx_blocking()) RCV_CUDA(cudaStreamSynchronize(c->stream));
+    return RCV_OK;
+  }
+  // host-resident (either side): software pipeline over the staging ring
+  Staged si[kRing], so[kRing];
+  const int depth = n < kRing ? n : kRing;
+  for (int k = 0; k < depth; ++k) {
+    RCV_TRY(stage_alloc(c, &srcs[k], SCR_STAGE_IN0 + k, &si[k]));
+    RCV_TRY(stage_alloc(c, &dsts[k], SCR_STAGE_OUT0 + 3 * k, &so[k]));
+  }
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) {
+    const int k = i % kRing;
+    Staged in = si[k], out = so[k];
+    if (!in.staged) in.v = view_of(&srcs[i], srcs[i].data, srcs[i].step);
+    if (!out.staged) out.v = view_of(&dsts[i], dsts[i].data, dsts[i].step);
+    if (i >= kRing) RCV_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_out[k], 0));  // slot k fully drained
+    RCV_TRY(copy_in(&srcs[i], in, c->s_in));
+    RCV_CUDA(cudaEventRecord(c->ev_in[k], c->s_in));
+    RCV_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+    RCV_TRY(launch(c, single(in.v), single(out.v), c->stream));
+    RCV_CUDA(cudaEventRecord(c->ev_k[k], c->stream));
+    RCV_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+    RCV_TRY(copy_out(&dsts[i], out, c->s_out));
+    RCV_CUDA(cudaEventRecord(c->ev_out[k], c->s_out));
+  }
+  RCV_CUDA(cudaStreamSynchronize(c->s_out));
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  RCV_CUDA(cudaStreamSynchronize(c->s_in));
+  return RCV_OK;
+}
+
+int check_cvt(const RcvMat *src, const RcvMat *dst, int code) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  int sc = 0, dc = 0;
+  switch (code) {
+    case RCV_COLOR_YUYV2BGR:
+    case RCV_COLOR_UYVY2BGR: sc = 2; dc = 3; break;
+    case RCV_COLOR_BGRA2BGR: sc = 4; dc = 3; break;
+    case RCV_COLOR_RGB2BGR: sc = 3; dc = 3; break;
+    case RCV_COLOR_BGR2GRAY: sc = 3; dc = 1; break;
+    case RCV_COLOR_BGR2XRGB32: sc = 3; dc = 4; break;
+    case RCV_COLOR_YUYV2GRAY: sc = 2; dc = 1; break;
+    default: return fail(RCV_ERR_ARG, "unknown colour conversion code %d", code);
+  }
+  if (src->depth != RCV_U8 || dst->depth != RCV_U8) return fail(RCV_ERR_DEPTH, "cvtColor: u8 only");
+  if (src->channels != sc || dst->channels != dc)
+    return fail(RCV_ERR_DEPTH, "cvtColor code %d wants %d -> %d channels, got %d -> %d", code, sc, dc, src->channels,
+                dst->channels);
+  if (code == RCV_COLOR_BGR2XRGB32 && dst->rows > 0 && ((dst->step & 3) || ((uintptr_t)dst->data & 3)))
+    return fail(RCV_ERR_SIZE, "XRGB32 dst must be 4-byte aligned");
+  return check_same_size(src, dst, "cvtColor");
+}
+
+int check_filter_pair(const RcvMat *src, const RcvMat *dst, const char *what) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (src->depth != dst->depth || src->channels != dst->channels)
+    return fail(RCV_ERR_DEPTH, "%s: dst depth/channels differ from src", what);
+  if (src->data == dst->data && src->rows > 0) return fail(RCV_ERR_ARG, "%s: in-place operation is not supported", what);
+  return check_same_size(src, dst, what);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- storage ---------------------------------------------------------------------------
+int rcv_mat_alloc_device_batch(RcvMat *mats, int32_t n, int32_t rows, int32_t cols, int32_t channels, int32_t depth,
+                               int32_t device) {
+  if (!mats || n < 1) return fail(RCV_ERR_ARG, "mats is NULL or n < 1");
+  if (rows < 0 || cols < 0 || channels < 1 || channels > 4 || (depth != RCV_U8 && depth != RCV_F32))
+    return fail(RCV_ERR_ARG, "bad geometry %dx%dx%d depth %d", rows, cols, channels, depth);
+  Ctx *c = device < 0 ? ctx_default() : ctx_get(device);
+  if (!c) return RCV_ERR_NOT_INIT;
+  size_t rb = (size_t)cols * channels * elem_size(depth);
+  size_t step = align_up(rb ? rb : 1, 256);
+  size_t frame = step * (size_t)(rows ? rows : 1);
+  void *p = nullptr;
+  RCV_CUDA(cudaMalloc(&p, frame * n));
+  for (int i = 0; i < n; ++i) {
+    mats[i].data = (uint8_t *)p + frame * i;
+    mats[i].rows = rows;
+    mats[i].cols = cols;
+    mats[i].step = step;
+    mats[i].channels = (uint8_t)channels;
+    mats[i].depth = (uint8_t)depth;
+    mats[i].loc = RCV_DEVICE;
+    mats[i].reserved = 0;
+    mats[i].device = c->device;
+  }
+  return RCV_OK;
+}
+
+int rcv_mat_alloc_device(RcvMat *m, int32_t rows, int32_t cols, int32_t channels, int32_t depth, int32_t device) {
+  return rcv_mat_alloc_device_batch(m, 1, rows, cols, channels, depth, device);
+}
+
+int rcv_mat_free_device_batch(RcvMat *mats, int32_t n) {
+  if (!mats || n < 1) return fail(RCV_ERR_ARG, "mats is NULL or n < 1");
+  if (mats[0].loc != RCV_DEVICE) return fail(RCV_ERR_ARG, "not a device Mat");
+  Ctx *c = ctx_get(mats[0].device);
+  if (!c) return RCV_ERR_NOT_INIT;
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  if (mats[0].data) RCV_CUDA(cudaFree(mats[0].data));
+  for (int i = 0; i < n; ++i) mats[i].data = nullptr;
+  return RCV_OK;
+}
+
+int rcv_mat_free_device(RcvMat *m) { return rcv_mat_free_device_batch(m, 1); }
+
+static int copy_mat(const RcvMat *src, RcvMat *dst, cudaMemcpyKind kind, int device) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (src->rows != dst->rows || src->cols != dst->cols || src->channels != dst->channels || src->depth != dst->depth)
+    return fail(RCV_ERR_SIZE, "upload/download: geometry differs");
+  Ctx *c = ctx_get(device);
+  if (!c) return RCV_ERR_NOT_INIT;
+  if (src->rows == 0 || src->cols == 0) return RCV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  RCV_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, src->data, src->step, mat_row_bytes(src), src->rows, kind, c->stream));
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  return RCV_OK;
+}
+
+int rcv_mat_upload(const RcvMat *host, RcvMat *dev) {
+  if (!host || !dev) return fail(RCV_ERR_ARG, "NULL Mat");
+  if (host->loc == RCV_DEVICE || dev->loc != RCV_DEVICE) return fail(RCV_ERR_ARG, "upload wants host -> device");
+  return copy_mat(host, dev, cudaMemcpyHostToDevice, dev->device);
+}
+
+int rcv_mat_download(const RcvMat *dev, RcvMat *host) {
+  if (!host || !dev) return fail(RCV_ERR_ARG, "NULL Mat");
+  if (host->loc == RCV_DEVICE || dev->loc != RCV_DEVICE) return fail(RCV_ERR_ARG, "download wants device -> host");
+  return copy_mat(dev, host, cudaMemcpyDeviceToHost, dev->device);
+}
+
+// ---- conversions -------------------------------------------------------------------------
+int rcv_cvt_color(const RcvMat *src, RcvMat *dst, int32_t code) {
+  RCV_TRY(check_cvt(src, dst, code));
+  return run_unary(src, dst, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_cvt(c, s, d, code, st);
+  });
+}
+
+int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code) {
+  if (n < 0 || (n > 0 && (!srcs || !dsts))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(dsts, n, "dsts"));
+  RCV_TRY(check_cvt(&srcs[0], &dsts[0], code));
+  return run_batch(srcs, dsts, n, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_cvt(c, s, d, code, st);
+  });
+}
+
+int rcv_yuyv_to_bgr(const RcvMat *src, RcvMat *dst) { return rcv_cvt_color(src, dst, RCV_COLOR_YUYV2BGR); }
+
+static int packed_cvt(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_len, size_t width, size_t height,
+                      int code) {
+  if (!src || !dst) return fail(RCV_ERR_ARG, "NULL buffer");
+  if (width > 0x7fffffffu / 4 || height > 0x7fffffffu || width * height > 0x7fffffffu / 4)
+    return fail(RCV_ERR_SIZE, "frame too large");
+  const size_t px = width * height;
+  RcvMat s, d;
+  memset(&s, 0, sizeof(s));
+  memset(&d, 0, sizeof(d));
+  if (code == RCV_COLOR_YUYV2BGR) {
+    // videoio/mod.rs:345-349: needs width*height*2 source bytes; converts width*height/2
+    // macro-pixels as ONE packed run (stride ignored), writing 6 bytes each.
+    const size_t pairs = px / 2;
+    if (src_len < px * 2) return fail(RCV_ERR_SIZE, "src has %zu bytes, frame needs %zu", src_len, px * 2);
+    if (dst_len < pairs * 6) return fail(RCV_ERR_SIZE, "dst has %zu bytes, needs %zu", dst_len, pairs * 6);
+    s.rows = 1;
+    s.cols = (int32_t)(pairs * 2);
+    s.channels = 2;
+    d.channels = 3;
+  } else {
+    if (src_len < px * 4 || dst_len < px * 3) return fail(RCV_ERR_SIZE, "buffer shorter than the %zux%zu frame", width, height);
+    s.rows = 1;
+    s.cols = (int32_t)px;
+    s.channels = 4;
+    d.channels = 3;
+  }
+  s.data = const_cast<uint8_t *>(src);
+  s.step = (size_t)s.cols * s.channels;
+  s.loc = RCV_HOST;
+  d.data = dst;
+  d.rows = 1;
+  d.cols = s.cols;
+  d.step = (size_t)d.cols * 3;
+  d.loc = RCV_HOST;
+  if (s.cols == 0) return RCV_OK;
+  return rcv_cvt_color(&s, &d, code);
+}
+
+int rcv_yuyv_to_bgr_packed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_len, size_t width,
+                           size_t height) {
+  return packed_cvt(src, src_len, dst, dst_len, width, height, RCV_COLOR_YUYV2BGR);
+}
+
+int rcv_bgra_to_bgr_packed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_len, size_t width,
+                           size_t height) {
+  return packed_cvt(src, src_len, dst, dst_len, width, height, RCV_COLOR_BGRA2BGR);
+}
+
+int rcv_nv12_to_bgr(const RcvMat *y, const RcvMat *uv, RcvMat *dst) {
+  RCV_TRY(check_mat(y, "y"));
+  RCV_TRY(check_mat(uv, "uv"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (y->depth != RCV_U8 || uv->depth != RCV_U8 || dst->depth != RCV_U8) return fail(RCV_ERR_DEPTH, "NV12: u8 only");
+  if (y->channels != 1 || uv->channels != 2 || dst->channels != 3) return fail(RCV_ERR_DEPTH, "NV12: want y c1, uv c2, dst c3");
+  if ((y->cols & 1) || (y->rows & 1)) return fail(RCV_ERR_SIZE, "NV12 needs even dimensions");
+  if (uv->rows != y->rows / 2 || uv->cols != y->cols / 2) return fail(RCV_ERR_SIZE, "uv plane must be rows/2 x cols/2");
+  RCV_TRY(check_same_size(y, dst, "nv12"));
+  const RcvMat *mats[3] = {y, uv, dst};
+  Ctx *c = pick_ctx(mats, 3);
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Staged sy, suv, so;
+  RCV_TRY(stage_alloc(c, y, SCR_STAGE_IN0, &sy));
+  RCV_TRY(stage_alloc(c, uv, SCR_STAGE_IN0 + 1, &suv));
+  RCV_TRY(stage_alloc(c, dst, SCR_STAGE_OUT0, &so));
+  RCV_TRY(copy_in(y, sy, c->stream));
+  RCV_TRY(copy_in(uv, suv, c->stream));
+  RCV_TRY(launch_nv12(c, sy.v, suv.v, so.v, c->stream));
+  RCV_TRY(copy_out(dst, so, c->stream));
+  if (ctx_blocking() || sy.staged || suv.staged || so.staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
+  return RCV_OK;
+}
+
+// ---- filters -------------------------------------------------------------------------------
+int rcv_gaussian_blur(const RcvMat *src, RcvMat *dst, int32_t kw, int32_t kh, double sigma_x, double sigma_y) {
+  RCV_TRY(check_filter_pair(src, dst, "GaussianBlur"));
+  return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
+  });
+}
+
+int rcv_gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t kw, int32_t kh, double sigma_x,
+                            double sigma_y) {
+  if (n < 0 || (n > 0 && (!srcs || !dsts))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(dsts, n, "dsts"));
+  RCV_TRY(check_filter_pair(&srcs[0], &dsts[0], "GaussianBlur"));
+  return run_batch(srcs, dsts, n, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
+  });
+}
+
+int rcv_sep_filter2d(const RcvMat *src, RcvMat *dst, const float *kx, int32_t kw, const float *ky, int32_t kh) {
+  RCV_TRY(check_filter_pair(src, dst, "sepFilter2D"));
+  if (!kx || !ky) return fail(RCV_ERR_ARG, "NULL taps");
+  if (src->depth != RCV_F32) return fail(RCV_ERR_DEPTH, "rcv_sep_filter2d is f32; use rcv_sep_filter2d_q8 for u8");
+  return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_sepfilter_f32(c, s, d, kx, kw, ky, kh, st);
+  });
+}
+
+int rcv_sep_filter2d_q8(const RcvMat *src, RcvMat *dst, const int32_t *kx, int32_t kw, const int32_t *ky, int32_t kh) {
+  RCV_TRY(check_filter_pair(src, dst, "sepFilter2D"));
+  if (!kx || !ky) return fail(RCV_ERR_ARG, "NULL taps");
+  if (src->depth != RCV_U8) return fail(RCV_ERR_DEPTH, "rcv_sep_filter2d_q8 is u8");
+  return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_sepfilter_q8(c, s, d, kx, kw, ky, kh, st);
+  });
+}
+
+int rcv_filter2d(const RcvMat *src, RcvMat *dst, const float *kernel, int32_t kw, int32_t kh, float delta) {
+  RCV_TRY(check_filter_pair(src, dst, "filter2D"));
+  if (!kernel) return fail(RCV_ERR_ARG, "NULL kernel");
+  return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_filter2d(c, s, d, kernel, kw, kh, delta, st);
+  });
+}
+
+static int check_sobel(const RcvMat *src, const RcvMat *mag, const RcvMat *gx, const RcvMat *gy) {
+  RCV_TRY(check_mat(src, "src"));
+  if (src->depth != RCV_F32 || src->channels != 1) return fail(RCV_ERR_DEPTH, "Sobel: single-channel f32 only");
+  if (!mag && !gx && !gy) return fail(RCV_ERR_ARG, "Sobel: no output requested");
+  const RcvMat *o[3] = {mag, gx, gy};
+  for (int k = 0; k < 3; ++k) {
+    if (!o[k]) continue;
+    RCV_TRY(check_mat(o[k], "out"));
+    if (o[k]->depth != RCV_F32 || o[k]->channels != 1) return fail(RCV_ERR_DEPTH, "Sobel: outputs are single-channel f32");
+    RCV_TRY(check_same_size(src, o[k], "Sobel"));
+    if (o[k]->data == src->data && src->rows > 0) return fail(RCV_ERR_ARG, "Sobel: in-place operation is not supported");
+  }
+  return RCV_OK;
+}
+
+int rcv_sobel_mag(const RcvMat *src, RcvMat *mag, RcvMat *gx, RcvMat *gy) {
+  RCV_TRY(check_sobel(src, mag, gx, gy));
+  const RcvMat *mats[4] = {src, mag, gx, gy};
+  Ctx *c = pick_ctx(mats, 4);
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Staged si, so[3];
+  RcvMat *o[3] = {mag, gx, gy};
+  DBatch ob[3];
+  bool any_staged = false;
+  RCV_TRY(stage_alloc(c, src, SCR_STAGE_IN0, &si));
+  for (int k = 0; k < 3; ++k) {
+    ob[k] = none_batch();
+    if (!o[k]) continue;
+    RCV_TRY(stage_alloc(c, o[k], SCR_STAGE_OUT0 + k, &so[k]));
+    ob[k] = single(so[k].v);
+    any_staged |= so[k].staged;
+  }
+  RCV_TRY(copy_in(src, si, c->stream));
+  RCV_TRY(launch_sobel(c, single(si.v), ob[0], ob[1], ob[2], c->stream));
+  for (int k = 0; k < 3; ++k)
+    if (o[k]) RCV_TRY(copy_out(o[k], so[k], c->stream));
+  if (ctx_blocking() || si.staged || any_staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
+  return RCV_OK;
+}
+
+int rcv_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
+  if (n < 0 || (n > 0 && (!srcs || !mags))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(mags, n, "mags"));
+  RCV_TRY(check_sobel(&srcs[0], &mags[0], nullptr, nullptr));
+  return run_batch(srcs, mags, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_sobel(c, s, d, none_batch(), none_batch(), st);
+  });
+}
+
+// ---- geometry --------------------------------------------------------------------------------
+static int check_resize(const RcvMat *src, const RcvMat *dst) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (src->depth != dst->depth || src->channels != dst->channels)
+    return fail(RCV_ERR_DEPTH, "resize: dst depth/channels differ from src");
+  if (dst->rows > 0 && dst->cols > 0 && (src->rows == 0 || src->cols == 0))
+    return fail(RCV_ERR_SIZE, "resize from an empty image");
+  if (src->data == dst->data && src->rows > 0) return fail(RCV_ERR_ARG, "resize: in-place operation is not supported");
+  return RCV_OK;
+}
+
+int rcv_resize_bilinear(const RcvMat *src, RcvMat *dst) {
+  RCV_TRY(check_resize(src, dst));
+  return run_unary(src, dst, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_resize(c, s, d, st);
+  });
+}
+
+int rcv_resize_bilinear_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n) {
+  if (n < 0 || (n > 0 && (!srcs || !dsts))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(dsts, n, "dsts"));
+  RCV_TRY(check_resize(&srcs[0], &dsts[0]));
+  return run_batch(srcs, dsts, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_resize(c, s, d, st);
+  });
+}
+
+static int check_warp(const RcvMat *src, const RcvMat *dst, const double M[6], int inverse_map, double iM[6]) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (!M) return fail(RCV_ERR_ARG, "M is NULL");
+  if (src->depth != dst->depth || src->channels != dst->channels)
+    return fail(RCV_ERR_DEPTH, "warpAffine: dst depth/channels differ from src");
+  if (src->depth == RCV_F32 && src->channels != 1) return fail(RCV_ERR_DEPTH, "warpAffine f32: single channel only");
+  if (src->data == dst->data && src->rows > 0) return fail(RCV_ERR_ARG, "warpAffine: in-place operation is not supported");
+  if (inverse_map) {
+    for (int i = 0; i < 6; ++i) iM[i] = M[i];
+  } else if (invert_affine(M, iM) != 0) {
+    return fail(RCV_ERR_ARG, "warpAffine: singular matrix");
+  }
+  return RCV_OK;
+}
+
+int rcv_warp_affine(const RcvMat *src, RcvMat *dst, const double M[6], int32_t inverse_map, double border_value) {
+  double iM[6];
+  RCV_TRY(check_warp(src, dst, M, inverse_map, iM));
+  return run_unary(src, dst, [&](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_warp_affine(c, s, d, iM, border_value, st);
+  });
+}
+
+int rcv_warp_affine_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const double M[6], int32_t inverse_map,
+                          double border_value) {
+  if (n < 0 || (n > 0 && (!srcs || !dsts))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(dsts, n, "dsts"));
+  double iM[6];
+  RCV_TRY(check_warp(&srcs[0], &dsts[0], M, inverse_map, iM));
+  return run_batch(srcs, dsts, n, [&](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_warp_affine(c, s, d, iM, border_value, st);
+  });
+}
+
+int rcv_get_rotation_matrix_2d(double cx, double cy, double angle_deg, double scale, double M[6]) {
+  if (!M) return fail(RCV_ERR_ARG, "M is NULL");
+  rotation_matrix(cx, cy, angle_deg, scale, M);
+  return RCV_OK;
+}
+
+int rcv_invert_affine(const double M[6], double iM[6]) {
+  if (!M || !iM) return fail(RCV_ERR_ARG, "NULL matrix");
+  if (invert_affine(M, iM) != 0) return fail(RCV_ERR_ARG, "singular matrix");
+  return RCV_OK;
+}
+
+// ---- fused chains ------------------------------------------------------------------------------
+int rcv_yuyv_to_bgr_gaussian5(const RcvMat *src, RcvMat *dst) {
+  RCV_TRY(check_cvt(src, dst, RCV_COLOR_YUYV2BGR));
+  return run_unary(src, dst, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_yuyv_gauss5(c, s, d, st);
+  });
+}
+
+}  // extern "C"

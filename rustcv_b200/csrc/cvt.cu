@@ -1,0 +1,331 @@
+// cvt.cu -- pixel-format conversion kernels (cvtColor family).
+//
+// These are the reference's real per-pixel loops:
+//   YUYV->BGR  rustcv/src/videoio/mod.rs:344-371  (twin rustcv-camera/src/decode.rs:160-191)
+//   clamp      rustcv/src/videoio/mod.rs:373-382
+//   BGRA->BGR  rustcv/src/videoio/mod.rs:385-399  (twin decode.rs:200-207)
+//   RGB<->BGR  rustcv-camera/src/decode.rs:213-219
+//   BGR->XRGB  rustcv/src/highgui/mod.rs:125-141
+//   NV12->BGR  rustcv-backend-msmf/examples/camera_view/convert.rs:46-86
+// All HBM-bound byte shuffling: one 16-byte-vector kernel per format when base
+// and step are 16-byte aligned, a scalar kernel otherwise.  Frames of a batch
+// are blockIdx.z.
+#include "rcv_internal.cuh"
+
+namespace rcv {
+
+// BT.601 integer formula, i32 math, arithmetic >> on negatives (videoio/mod.rs:352-369).
+__device__ __forceinline__ uint32_t clamp_u8(int v) { return (uint32_t)min(max(v, 0), 255); }
+
+struct Bgr2 {
+  uint32_t b0, g0, r0, b1, g1, r1;
+};
+
+__device__ __forceinline__ Bgr2 yuv_pair(int y0, int ub, int y1, int vb) {
+  int u = ub - 128, v = vb - 128;
+  int c0 = 298 * (y0 - 16) + 128, c1 = 298 * (y1 - 16) + 128;
+  int db = 516 * u, dg = -100 * u - 208 * v, dr = 409 * v;
+  Bgr2 o;
+  o.b0 = clamp_u8((c0 + db) >> 8);
+  o.g0 = clamp_u8((c0 + dg) >> 8);
+  o.r0 = clamp_u8((c0 + dr) >> 8);
+  o.b1 = clamp_u8((c1 + db) >> 8);
+  o.g1 = clamp_u8((c1 + dg) >> 8);
+  o.r1 = clamp_u8((c1 + dr) >> 8);
+  return o;
+}
+
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
+  return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+}
+
+struct CvtArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int rows, cols;
+};
+
+// ---- scalar kernels: one thread per pixel / macro-pixel ------------------------------
+template <int CODE>
+__global__ void __launch_bounds__(256) k_cvt_scalar(CvtArgs a) {
+  int r = blockIdx.y;
+  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (CODE == RCV_COLOR_YUYV2BGR || CODE == RCV_COLOR_UYVY2BGR || CODE == RCV_COLOR_YUYV2GRAY) {
+    if (i >= a.cols / 2) return;
+    int q0 = s[i * 4], q1 = s[i * 4 + 1], q2 = s[i * 4 + 2], q3 = s[i * 4 + 3];
+    Bgr2 o = (CODE == RCV_COLOR_UYVY2BGR) ? yuv_pair(q1, q0, q3, q2) : yuv_pair(q0, q1, q2, q3);
+    if (CODE == RCV_COLOR_YUYV2GRAY) {
+      d[i * 2] = (uint8_t)gray_of(o.b0, o.g0, o.r0);
+      d[i * 2 + 1] = (uint8_t)gray_of(o.b1, o.g1, o.r1);
+    } else {
+      d[i * 6 + 0] = (uint8_t)o.b0;
+      d[i * 6 + 1] = (uint8_t)o.g0;
+      d[i * 6 + 2] = (uint8_t)o.r0;
+      d[i * 6 + 3] = (uint8_t)o.b1;
+      d[i * 6 + 4] = (uint8_t)o.g1;
+      d[i * 6 + 5] = (uint8_t)o.r1;
+    }
+  } else {
+    if (i >= a.cols) return;
+    if (CODE == RCV_COLOR_BGRA2BGR) {
+      d[i * 3] = s[i * 4];
+      d[i * 3 + 1] = s[i * 4 + 1];
+      d[i * 3 + 2] = s[i * 4 + 2];
+    } else if (CODE == RCV_COLOR_RGB2BGR) {
+      uint8_t b0 = s[i * 3], b1 = s[i * 3 + 1], b2 = s[i * 3 + 2];
+      d[i * 3] = b2;
+      d[i * 3 + 1] = b1;
+      d[i * 3 + 2] = b0;
+    } else if (CODE == RCV_COLOR_BGR2GRAY) {
+      d[i] = (uint8_t)gray_of(s[i * 3], s[i * 3 + 1], s[i * 3 + 2]);
+    } else if (CODE == RCV_COLOR_BGR2XRGB32) {
+      ((uint32_t *)d)[i] = ((uint32_t)s[i * 3 + 2] << 16) | ((uint32_t)s[i * 3 + 1] << 8) | s[i * 3];
+    }
+  }
+}
+
+// ---- vector kernels ---------------------------------------------------------------------
+// byte k of a little-endian word array
+__device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu; }
+
+// YUYV/UYVY -> BGR: a thread converts 8 macro-pixels: 32 B in (2 x LDG.128) -> 48 B out (3 x STG.128).
+// -> GRAY: 16 px -> 16 B out.
+template <int CODE>
+__global__ void __launch_bounds__(128) k_yuv422_vec(CvtArgs a) {
+  int r = blockIdx.y;
+  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int pairs = a.cols / 2;
+  if (g * 8 >= pairs) return;
+  if (g * 8 + 8 <= pairs) {
+    uint4 q0 = __ldg((const uint4 *)(s + (size_t)g * 32));
+    uint4 q1 = __ldg((const uint4 *)(s + (size_t)g * 32 + 16));
+    uint32_t in[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t out[12];
+    uint32_t gr[4];
+    uint8_t ob[48];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      uint32_t w = in[p];
+      int b0 = w & 0xFF, b1 = (w >> 8) & 0xFF, b2 = (w >> 16) & 0xFF, b3 = w >> 24;
+      Bgr2 o = (CODE == RCV_COLOR_UYVY2BGR) ? yuv_pair(b1, b0, b3, b2) : yuv_pair(b0, b1, b2, b3);
+      if (CODE == RCV_COLOR_YUYV2GRAY) {
+        ob[p * 2] = (uint8_t)gray_of(o.b0, o.g0, o.r0);
+        ob[p * 2 + 1] = (uint8_t)gray_of(o.b1, o.g1, o.r1);
+      } else {
+        ob[p * 6 + 0] = (uint8_t)o.b0;
+        ob[p * 6 + 1] = (uint8_t)o.g0;
+        ob[p * 6 + 2] = (uint8_t)o.r0;
+        ob[p * 6 + 3] = (uint8_t)o.b1;
+        ob[p * 6 + 4] = (uint8_t)o.g1;
+        ob[p * 6 + 5] = (uint8_t)o.r1;
+      }
+    }
+    if (CODE == RCV_COLOR_YUYV2GRAY) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        gr[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | ((uint32_t)ob[4 * k + 3] << 24);
+      *(uint4 *)(d + (size_t)g * 16) = make_uint4(gr[0], gr[1], gr[2], gr[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        out[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | ((uint32_t)ob[4 * k + 3] << 24);
+      uint4 *dp = (uint4 *)(d + (size_t)g * 48);
+      dp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+      dp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+      dp[2] = make_uint4(out[8], out[9], out[10], out[11]);
+    }
+  } else {
+    for (int i = g * 8; i < pairs; ++i) {
+      int q0 = s[i * 4], q1 = s[i * 4 + 1], q2 = s[i * 4 + 2], q3 = s[i * 4 + 3];
+      Bgr2 o = (CODE == RCV_COLOR_UYVY2BGR) ? yuv_pair(q1, q0, q3, q2) : yuv_pair(q0, q1, q2, q3);
+      if (CODE == RCV_COLOR_YUYV2GRAY) {
+        d[i * 2] = (uint8_t)gray_of(o.b0, o.g0, o.r0);
+        d[i * 2 + 1] = (uint8_t)gray_of(o.b1, o.g1, o.r1);
+      } else {
+        d[i * 6 + 0] = (uint8_t)o.b0;
+        d[i * 6 + 1] = (uint8_t)o.g0;
+        d[i * 6 + 2] = (uint8_t)o.r0;
+        d[i * 6 + 3] = (uint8_t)o.b1;
+        d[i * 6 + 4] = (uint8_t)o.g1;
+        d[i * 6 + 5] = (uint8_t)o.r1;
+      }
+    }
+  }
+}
+
+// 16 pixels per thread for the 3/4-byte formats.
+//   BGRA2BGR   64 B in -> 48 B out      RGB2BGR 48 -> 48
+//   BGR2GRAY   48 B in -> 16 B out      BGR2XRGB32 48 -> 64
+template <int CODE>
+__global__ void __launch_bounds__(128) k_px16_vec(CvtArgs a) {
+  constexpr int IN_B = (CODE == RCV_COLOR_BGRA2BGR) ? 64 : 48;
+  constexpr int OUT_B = (CODE == RCV_COLOR_BGRA2BGR || CODE == RCV_COLOR_RGB2BGR) ? 48
+                        : (CODE == RCV_COLOR_BGR2GRAY)                            ? 16
+                                                                                  : 64;
+  constexpr int IN_PX = IN_B / 16, OUT_PX = OUT_B / 16;  // bytes per pixel
+  int r = blockIdx.y;
+  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 16 >= a.cols) return;
+  if (g * 16 + 16 <= a.cols) {
+    uint32_t in[IN_B / 4], out[OUT_B / 4];
+    const uint4 *sp = (const uint4 *)(s + (size_t)g * IN_B);
+#pragma unroll
+    for (int k = 0; k < IN_B / 16; ++k) {
+      uint4 q = __ldg(sp + k);
+      in[4 * k] = q.x;
+      in[4 * k + 1] = q.y;
+      in[4 * k + 2] = q.z;
+      in[4 * k + 3] = q.w;
+    }
+    if (CODE == RCV_COLOR_BGR2XRGB32) {
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        out[p] = (byte_of(in, p * 3 + 2) << 16) | (byte_of(in, p * 3 + 1) << 8) | byte_of(in, p * 3);
+    } else if (CODE == RCV_COLOR_BGR2GRAY) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int p = 4 * k + j;
+          w |= gray_of(byte_of(in, p * 3), byte_of(in, p * 3 + 1), byte_of(in, p * 3 + 2)) << (8 * j);
+        }
+        out[k] = w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < OUT_B / 4; ++k) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int ob = 4 * k + j;  // output byte index
+          int p = ob / 3, c = ob % 3;
+          int sc = (CODE == RCV_COLOR_RGB2BGR) ? 2 - c : c;
+          w |= byte_of(in, p * IN_PX + sc) << (8 * j);
+        }
+        out[k] = w;
+      }
+    }
+    uint4 *dp = (uint4 *)(d + (size_t)g * OUT_B);
+#pragma unroll
+    for (int k = 0; k < OUT_B / 16; ++k) dp[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+  } else {
+    for (int i = g * 16; i < a.cols; ++i) {
+      const uint8_t *sp = s + (size_t)i * IN_PX;
+      if (CODE == RCV_COLOR_BGRA2BGR) {
+        d[i * 3] = sp[0];
+        d[i * 3 + 1] = sp[1];
+        d[i * 3 + 2] = sp[2];
+      } else if (CODE == RCV_COLOR_RGB2BGR) {
+        uint8_t b0 = sp[0], b1 = sp[1], b2 = sp[2];
+        d[i * 3] = b2;
+        d[i * 3 + 1] = b1;
+        d[i * 3 + 2] = b0;
+      } else if (CODE == RCV_COLOR_BGR2GRAY) {
+        d[i] = (uint8_t)gray_of(sp[0], sp[1], sp[2]);
+      } else {
+        ((uint32_t *)d)[i] = ((uint32_t)sp[2] << 16) | ((uint32_t)sp[1] << 8) | sp[0];
+      }
+    }
+  }
+  (void)OUT_PX;
+}
+
+// NV12 -> BGR, per-pixel formula of convert.rs:46-86 (uv_row = row/2, uv_col = col/2).
+struct Nv12Args {
+  const uint8_t *y;
+  size_t ystep;
+  const uint8_t *uv;
+  size_t uvstep;
+  uint8_t *dst;
+  size_t dstep;
+  int rows, cols;
+};
+
+__global__ void __launch_bounds__(256) k_nv12(Nv12Args a) {
+  int r = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // pixel pair
+  int c0 = i * 2;
+  if (c0 >= a.cols) return;
+  const uint8_t *yr = a.y + (size_t)r * a.ystep;
+  const uint8_t *uvr = a.uv + (size_t)(r / 2) * a.uvstep;
+  uint8_t *d = a.dst + (size_t)r * a.dstep;
+  int y0 = yr[c0];
+  int y1 = (c0 + 1 < a.cols) ? yr[c0 + 1] : 16;
+  Bgr2 o = yuv_pair(y0, uvr[c0], y1, uvr[c0 + 1]);
+  d[c0 * 3] = (uint8_t)o.b0;
+  d[c0 * 3 + 1] = (uint8_t)o.g0;
+  d[c0 * 3 + 2] = (uint8_t)o.r0;
+  if (c0 + 1 < a.cols) {
+    d[c0 * 3 + 3] = (uint8_t)o.b1;
+    d[c0 * 3 + 4] = (uint8_t)o.g1;
+    d[c0 * 3 + 5] = (uint8_t)o.r1;
+  }
+}
+
+static bool aligned16(const DBatch &b) {
+  return (((uintptr_t)b.v.data | b.v.step | b.frame_stride) & 15) == 0;
+}
+
+template <int CODE>
+static int launch_code(const DBatch &src, const DBatch &dst, cudaStream_t s) {
+  CvtArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows, src.v.cols};
+  bool vec = aligned16(src) && aligned16(dst);
+  constexpr bool yuv = (CODE == RCV_COLOR_YUYV2BGR || CODE == RCV_COLOR_UYVY2BGR || CODE == RCV_COLOR_YUYV2GRAY);
+  if (vec) {
+    if constexpr (yuv) {
+      int groups = ceil_div(src.v.cols / 2, 8);
+      if (groups == 0) return RCV_OK;
+      dim3 grid(ceil_div(groups, 128), src.v.rows, src.n);
+      k_yuv422_vec<CODE><<<grid, 128, 0, s>>>(a);
+    } else {
+      int groups = ceil_div(src.v.cols, 16);
+      dim3 grid(ceil_div(groups, 128), src.v.rows, src.n);
+      k_px16_vec<CODE><<<grid, 128, 0, s>>>(a);
+    }
+  } else {
+    int items = yuv ? src.v.cols / 2 : src.v.cols;
+    if (items == 0) return RCV_OK;
+    dim3 grid(ceil_div(items, 256), src.v.rows, src.n);
+    k_cvt_scalar<CODE><<<grid, 256, 0, s>>>(a);
+  }
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+int launch_cvt(Ctx *, const DBatch &src, const DBatch &dst, int code, cudaStream_t s) {
+  if (src.v.rows > 65535 || src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "rows/frames > 65535");
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  switch (code) {
+    case RCV_COLOR_YUYV2BGR: return launch_code<RCV_COLOR_YUYV2BGR>(src, dst, s);
+    case RCV_COLOR_UYVY2BGR: return launch_code<RCV_COLOR_UYVY2BGR>(src, dst, s);
+    case RCV_COLOR_BGRA2BGR: return launch_code<RCV_COLOR_BGRA2BGR>(src, dst, s);
+    case RCV_COLOR_RGB2BGR: return launch_code<RCV_COLOR_RGB2BGR>(src, dst, s);
+    case RCV_COLOR_BGR2GRAY: return launch_code<RCV_COLOR_BGR2GRAY>(src, dst, s);
+    case RCV_COLOR_BGR2XRGB32: return launch_code<RCV_COLOR_BGR2XRGB32>(src, dst, s);
+    case RCV_COLOR_YUYV2GRAY: return launch_code<RCV_COLOR_YUYV2GRAY>(src, dst, s);
+  }
+  return fail(RCV_ERR_ARG, "unknown colour conversion code %d", code);
+}
+
+int launch_nv12(Ctx *, const DView &y, const DView &uv, const DView &dst, cudaStream_t s) {
+  if (y.rows > 65535) return fail(RCV_ERR_UNSUPPORTED, "rows > 65535");
+  if (y.rows == 0 || y.cols == 0) return RCV_OK;
+  Nv12Args a{y.data, y.step, uv.data, uv.step, dst.data, dst.step, y.rows, y.cols};
+  dim3 grid(ceil_div(ceil_div(y.cols, 2), 256), y.rows, 1);
+  k_nv12<<<grid, 256, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+}  // namespace rcv

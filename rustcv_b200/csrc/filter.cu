@@ -1,0 +1,405 @@
+// filter.cu -- generic (any taps, any geometry) filters: separable u8 Q8, separable f32,
+// dense filter2D, and the small-image Sobel.  These are the general-case companions of
+// the strip-pipeline kernels in stencil.cu; they take every size/alignment, including
+// 1-row / 1-column images, and define BORDER_REFLECT_101 by index arithmetic.
+//
+// The reference has no filters (rustcv/src/imgproc/mod.rs:1-4); semantics and operation
+// order are the oracle's: orc_sepfilter_u8_q8, orc_sepfilter_f32, orc_filter2d_{f32,u8},
+// orc_sobel3_f32 in oracle/rcv_oracle.c.
+#include "rcv_internal.cuh"
+
+#include <cmath>
+
+namespace rcv {
+
+constexpr int kMaxTaps = 31;
+
+// ---------------------------------------------------------------------------------------
+// separable filter: CTA tile of TBX element-columns x TBY rows.
+//   stage 1  raw tile (+ halo, reflected) -> shared
+//   stage 2  horizontal pass              -> shared (accumulator type)
+//   stage 3  vertical pass                -> global
+// "element column" = index into the row in elements (pixel*cn + channel); the horizontal
+// tap j reads element column x + (j - rx)*cn.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct SepTraits;
+template <>
+struct SepTraits<uint8_t> {
+  typedef uint32_t Acc;
+  typedef int32_t Tap;
+};
+template <>
+struct SepTraits<float> {
+  typedef float Acc;
+  typedef float Tap;
+};
+
+template <typename T>
+struct SepArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int rows, cols, cn;
+  int kw, kh;
+  typename SepTraits<T>::Tap kx[kMaxTaps + 1], ky[kMaxTaps + 1];
+};
+
+constexpr int kSepTBX = 128, kSepTBY = 32, kSepThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kSepThreads) k_sepfilter(const SepArgs<T> a) {
+  typedef typename SepTraits<T>::Acc Acc;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int rx = a.kw / 2, ry = a.kh / 2;
+  const int halo_x = (a.kw - 1) * a.cn;
+  const int RW = kSepTBX + halo_x;     // raw tile width (elements)
+  const int RH = kSepTBY + a.kh - 1;   // raw tile height
+  T *raw = (T *)smem;
+  Acc *mid = (Acc *)(smem + (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15));
+
+  const int ncols = a.cols * a.cn;
+  const int ex0 = blockIdx.x * kSepTBX;  // first element column of the tile
+  const int y0 = blockIdx.y * kSepTBY;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
+
+  // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][reflect_px(ex0 + x - rx*cn)]
+  for (int i = threadIdx.x; i < RW * RH; i += kSepThreads) {
+    int r = i / RW, x = i - r * RW;
+    int ex = ex0 + x - rx * a.cn;
+    // floor division for negatives
+    int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
+    int ch = ex - px * a.cn;
+    int sy = reflect101(y0 + r - ry, a.rows);
+    int sx = reflect101(px, a.cols);
+    raw[i] = ((const T *)(src + (size_t)sy * a.sstep))[sx * a.cn + ch];
+  }
+  __syncthreads();
+  // stage 2: horizontal
+  for (int i = threadIdx.x; i < kSepTBX * RH; i += kSepThreads) {
+    int r = i / kSepTBX, x = i - r * kSepTBX;
+    const T *p = raw + r * RW + x;
+    Acc acc = 0;
+    for (int j = 0; j < a.kw; ++j) {
+      if (sizeof(T) == 1)
+        acc += (Acc)a.kx[j] * (Acc)p[j * a.cn];
+      else
+        acc = fmaf((float)a.kx[j], (float)p[j * a.cn], (float)acc);
+    }
+    mid[i] = acc;
+  }
+  __syncthreads();
+  // stage 3: vertical
+  for (int i = threadIdx.x; i < kSepTBX * kSepTBY; i += kSepThreads) {
+    int r = i / kSepTBX, x = i - r * kSepTBX;
+    int y = y0 + r, ex = ex0 + x;
+    if (y >= a.rows || ex >= ncols) continue;
+    const Acc *p = mid + r * kSepTBX + x;
+    if (sizeof(T) == 1) {
+      uint32_t acc = 32768u;
+      for (int k = 0; k < a.kh; ++k) acc += (uint32_t)a.ky[k] * (uint32_t)p[k * kSepTBX];
+      acc >>= 16;
+      ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)(acc > 255u ? 255u : acc);
+    } else {
+      float acc = 0.0f;
+      for (int k = 0; k < a.kh; ++k) acc = fmaf((float)a.ky[k], (float)p[k * kSepTBX], acc);
+      ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+    }
+  }
+}
+
+template <typename T>
+static int launch_sep(const DBatch &src, const DBatch &dst, const typename SepTraits<T>::Tap *kx, int kw,
+                      const typename SepTraits<T>::Tap *ky, int kh, cudaStream_t s) {
+  if (kw < 1 || kh < 1 || kw > kMaxTaps || kh > kMaxTaps)
+    return fail(RCV_ERR_ARG, "kernel size %dx%d outside 1..%d", kw, kh, kMaxTaps);
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  SepArgs<T> a;
+  a.src = src.v.data;
+  a.sstep = src.v.step;
+  a.sfs = src.frame_stride;
+  a.dst = dst.v.data;
+  a.dstep = dst.v.step;
+  a.dfs = dst.frame_stride;
+  a.rows = src.v.rows;
+  a.cols = src.v.cols;
+  a.cn = src.v.cn;
+  a.kw = kw;
+  a.kh = kh;
+  for (int i = 0; i < kw; ++i) a.kx[i] = kx[i];
+  for (int i = 0; i < kh; ++i) a.ky[i] = ky[i];
+  const int RW = kSepTBX + (kw - 1) * a.cn, RH = kSepTBY + kh - 1;
+  size_t smem = (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15) + (size_t)kSepTBX * RH * 4;
+  auto kern = k_sepfilter<T>;
+  RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ncols = a.cols * a.cn;
+  dim3 grid(ceil_div(ncols, kSepTBX), ceil_div(a.rows, kSepTBY), src.n);
+  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  kern<<<grid, kSepThreads, smem, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+int launch_sepfilter_q8(Ctx *, const DBatch &src, const DBatch &dst, const int32_t *kx, int kw, const int32_t *ky,
+                        int kh, cudaStream_t s) {
+  return launch_sep<uint8_t>(src, dst, kx, kw, ky, kh, s);
+}
+
+int launch_sepfilter_f32(Ctx *, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky,
+                         int kh, cudaStream_t s) {
+  return launch_sep<float>(src, dst, kx, kw, ky, kh, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// GaussianBlur front end (cv::GaussianBlur model, oracle: orc_gaussian_blur_{u8,f32})
+// ---------------------------------------------------------------------------------------
+int gaussian_ksize(double sigma, bool is_u8) {
+  int k = (int)lrint(sigma * (is_u8 ? 3 : 4) * 2 + 1);
+  return k | 1;
+}
+
+void gaussian_kernel_f64(int n, double sigma, double *kd) {
+  static const double t1[] = {1.0};
+  static const double t3[] = {0.25, 0.5, 0.25};
+  static const double t5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
+  static const double t7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+  if (sigma <= 0 && n <= 7 && (n & 1)) {
+    const double *t = n == 1 ? t1 : n == 3 ? t3 : n == 5 ? t5 : t7;
+    for (int i = 0; i < n; ++i) kd[i] = t[i];
+    return;
+  }
+  double sig = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+  double scale2x = -0.5 / (sig * sig);
+  double sum = 0;
+  for (int i = 0; i < n; ++i) {
+    double x = i - (n - 1) * 0.5;
+    kd[i] = exp(scale2x * x * x);
+    sum += kd[i];
+  }
+  for (int i = 0; i < n; ++i) kd[i] /= sum;
+}
+
+void gaussian_kernel_q8(int n, double sigma, int32_t *kq) {
+  double kd[kMaxTaps + 1];
+  gaussian_kernel_f64(n, sigma, kd);
+  int n2 = n / 2;
+  double err = 0;
+  int sum = 0;
+  for (int i = 0; i < n2; ++i) {
+    double adj = kd[i] * 256.0 + err;
+    int v0 = (int)lrint(adj);
+    err = adj - v0;
+    kq[i] = v0;
+    kq[n - 1 - i] = v0;
+    sum += v0;
+  }
+  kq[n2] = 256 - 2 * sum;
+}
+
+int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+
+int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh, double sx, double sy,
+                    cudaStream_t s) {
+  const bool u8 = src.v.depth == RCV_U8;
+  if (sy <= 0) sy = sx;
+  if (kw <= 0 && sx > 0) kw = gaussian_ksize(sx, u8);
+  if (kh <= 0 && sy > 0) kh = gaussian_ksize(sy, u8);
+  if (kw < 1 || kh < 1 || !(kw & 1) || !(kh & 1) || kw > kMaxTaps || kh > kMaxTaps)
+    return fail(RCV_ERR_ARG, "GaussianBlur needs odd kernel sizes in 1..%d (got %dx%d)", kMaxTaps, kw, kh);
+  if (u8) {
+    int32_t kx[kMaxTaps + 1], ky[kMaxTaps + 1];
+    gaussian_kernel_q8(kw, sx, kx);
+    gaussian_kernel_q8(kh, sy, ky);
+    const bool binomial5 = kw == 5 && kh == 5 && kx[0] == 16 && kx[1] == 64 && kx[2] == 96 && ky[0] == 16 &&
+                           ky[1] == 64 && ky[2] == 96;
+    if (binomial5 && opt_get("gauss.force_generic", 0) == 0) {
+      int rc = launch_gauss5_strip(c, src, dst, s);
+      if (rc != RCV_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_sepfilter_q8(c, src, dst, kx, kw, ky, kh, s);
+  }
+  double kd[kMaxTaps + 1];
+  float kx[kMaxTaps + 1], ky[kMaxTaps + 1];
+  gaussian_kernel_f64(kw, sx, kd);
+  for (int i = 0; i < kw; ++i) kx[i] = (float)kd[i];
+  gaussian_kernel_f64(kh, sy, kd);
+  for (int i = 0; i < kh; ++i) ky[i] = (float)kd[i];
+  return launch_sepfilter_f32(c, src, dst, kx, kw, ky, kh, s);
+}
+
+// YUYV -> BGR -> GaussianBlur 5x5.  Two kernels over a device-resident intermediate (no
+// host round trip); the single-kernel fusion is SURVEY.md section 8f rank 1.
+int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  DBatch tmp = dst;
+  size_t pitch = (dst.v.row_bytes() + 255) / 256 * 256;
+  size_t frame = pitch * (size_t)dst.v.rows;
+  void *p = nullptr;
+  RCV_TRY(ctx_scratch(c, SCR_FUSE_TMP, frame * src.n, &p));
+  tmp.v.data = (uint8_t *)p;
+  tmp.v.step = pitch;
+  tmp.frame_stride = src.n > 1 ? frame : 0;
+  RCV_TRY(launch_cvt(c, src, tmp, RCV_COLOR_YUYV2BGR, s));
+  // an odd trailing column is left untouched by the conversion (cols/2 macro-pixels per row)
+  return launch_gaussian(c, tmp, dst, 5, 5, 0.0, 0.0, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// dense filter2D (correlation, anchor = centre, REFLECT_101)
+//   acc = delta; acc = fmaf(k[i][j], p, acc) in row-major tap order
+//   u8: saturate(rint(acc)) (round half even)
+// ---------------------------------------------------------------------------------------
+struct F2dArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int rows, cols, cn;
+  int kw, kh;
+  const float *taps;  // device, kh*kw
+  float delta;
+};
+
+constexpr int kF2dTBX = 64, kF2dTBY = 16, kF2dThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int rx = a.kw / 2, ry = a.kh / 2;
+  const int RW = kF2dTBX + (a.kw - 1) * a.cn;
+  const int RH = kF2dTBY + a.kh - 1;
+  float *taps = (float *)smem;
+  T *raw = (T *)(smem + (((size_t)a.kw * a.kh * 4 + 15) & ~(size_t)15));
+  const int ncols = a.cols * a.cn;
+  const int ex0 = blockIdx.x * kF2dTBX, y0 = blockIdx.y * kF2dTBY;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
+  for (int i = threadIdx.x; i < a.kw * a.kh; i += kF2dThreads) taps[i] = a.taps[i];
+  for (int i = threadIdx.x; i < RW * RH; i += kF2dThreads) {
+    int r = i / RW, x = i - r * RW;
+    int ex = ex0 + x - rx * a.cn;
+    int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
+    int ch = ex - px * a.cn;
+    int sy = reflect101(y0 + r - ry, a.rows);
+    int sx = reflect101(px, a.cols);
+    raw[i] = ((const T *)(src + (size_t)sy * a.sstep))[sx * a.cn + ch];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kF2dTBX * kF2dTBY; i += kF2dThreads) {
+    int r = i / kF2dTBX, x = i - r * kF2dTBX;
+    int y = y0 + r, ex = ex0 + x;
+    if (y >= a.rows || ex >= ncols) continue;
+    float acc = a.delta;
+    for (int ki = 0; ki < a.kh; ++ki) {
+      const T *p = raw + (r + ki) * RW + x;
+      const float *t = taps + ki * a.kw;
+      for (int kj = 0; kj < a.kw; ++kj) acc = fmaf(t[kj], (float)p[kj * a.cn], acc);
+    }
+    if (sizeof(T) == 1) {
+      int v = __float2int_rn(acc);  // round half to even, saturating conversion
+      ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)min(max(v, 0), 255);
+    } else {
+      ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+    }
+  }
+}
+
+int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                    cudaStream_t s) {
+  if (kw < 1 || kh < 1 || kw > kMaxTaps || kh > kMaxTaps)
+    return fail(RCV_ERR_ARG, "kernel size %dx%d outside 1..%d", kw, kh, kMaxTaps);
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  void *dtaps = nullptr;
+  RCV_TRY(ctx_scratch(c, SCR_TAPS, (size_t)kw * kh * sizeof(float), &dtaps));
+  RCV_CUDA(cudaMemcpyAsync(dtaps, k, (size_t)kw * kh * sizeof(float), cudaMemcpyHostToDevice, s));
+  F2dArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows,
+            src.v.cols, src.v.cn, kw, kh, (const float *)dtaps, delta};
+  const size_t es = src.v.elem();
+  const int RW = kF2dTBX + (kw - 1) * a.cn, RH = kF2dTBY + kh - 1;
+  size_t smem = (((size_t)kw * kh * 4 + 15) & ~(size_t)15) + (size_t)RW * RH * es;
+  dim3 grid(ceil_div(a.cols * a.cn, kF2dTBX), ceil_div(a.rows, kF2dTBY), src.n);
+  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  if (src.v.depth == RCV_U8) {
+    RCV_CUDA(cudaFuncSetAttribute(k_filter2d<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_filter2d<uint8_t><<<grid, kF2dThreads, smem, s>>>(a);
+  } else {
+    RCV_CUDA(cudaFuncSetAttribute(k_filter2d<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_filter2d<float><<<grid, kF2dThreads, smem, s>>>(a);
+  }
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Sobel 3x3 + magnitude, general geometry (one thread per pixel; index-arithmetic borders).
+// Same operation order as Sobel3Op in stencil.cu and orc_sobel3_f32.
+// ---------------------------------------------------------------------------------------
+struct SobelArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *out[3];  // mag, gx, gy
+  size_t ostep[3], ofs[3];
+  int rows, cols;
+};
+
+__global__ void __launch_bounds__(256) k_sobel_generic(const SobelArgs a) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= a.cols) return;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const float *pm = (const float *)(src + (size_t)reflect101(y - 1, a.rows) * a.sstep);
+  const float *p0 = (const float *)(src + (size_t)y * a.sstep);
+  const float *pp = (const float *)(src + (size_t)reflect101(y + 1, a.rows) * a.sstep);
+  int xs[3] = {reflect101(x - 1, a.cols), x, reflect101(x + 1, a.cols)};
+  float s[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float t = __fadd_rn(pm[xs[k]], pp[xs[k]]);
+    float u = __fmul_rn(2.0f, p0[xs[k]]);
+    s[k] = __fadd_rn(t, u);
+    d[k] = __fsub_rn(pp[xs[k]], pm[xs[k]]);
+  }
+  float gx = __fsub_rn(s[2], s[0]);
+  float gy = __fadd_rn(__fadd_rn(d[0], d[2]), __fmul_rn(2.0f, d[1]));
+  float mg = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+  float res[3] = {mg, gx, gy};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (a.out[k]) ((float *)(a.out[k] + (size_t)blockIdx.z * a.ofs[k] + (size_t)y * a.ostep[k]))[x] = res[k];
+}
+
+int launch_sobel_strip(Ctx *c, const DBatch &src, const DBatch &mag, const DBatch &gx, const DBatch &gy,
+                       cudaStream_t s);
+
+int launch_sobel(Ctx *c, const DBatch &src, const DBatch &mag, const DBatch &gx, const DBatch &gy,
+                 cudaStream_t s) {
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (opt_get("sobel.force_generic", 0) == 0) {
+    int rc = launch_sobel_strip(c, src, mag, gx, gy, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
+  if (src.v.rows > 65535 || src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  SobelArgs a;
+  a.src = src.v.data;
+  a.sstep = src.v.step;
+  a.sfs = src.frame_stride;
+  const DBatch *o[3] = {&mag, &gx, &gy};
+  for (int k = 0; k < 3; ++k) {
+    a.out[k] = o[k]->v.data;
+    a.ostep[k] = o[k]->v.step;
+    a.ofs[k] = o[k]->frame_stride;
+  }
+  a.rows = src.v.rows;
+  a.cols = src.v.cols;
+  dim3 grid(ceil_div(a.cols, 256), a.rows, src.n);
+  k_sobel_generic<<<grid, 256, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+}  // namespace rcv

@@ -1,0 +1,310 @@
+// geom.cu -- bilinear resize and warpAffine.
+//
+// Absent from the reference (the only "resize" is a vendor call,
+// rustcv-camera/src/backend/macos/bridge.m:140); semantics are the oracle's
+// (oracle/rcv_oracle.c: orc_resize_bilinear_{u8,f32}, orc_warp_affine_{f32,u8}):
+//   resize u8   cv::resize INTER_LINEAR fixed point (11-bit weights), bit-exact with OpenCV
+//   resize f32  h = p0*(1-fx) + p1*fx ; out = h0*(1-fy) + h1*fy, each op rounded once
+//   warpAffine  inverse map, f64 row term, fmaf column term, fmaf lerp chain, constant border
+// All gather kernels: HBM/L2-bound, no shared-memory staging needed for the general case;
+// the exact 4x BGR downscale (BASELINE.json config 4) has a 128-bit-load specialisation.
+#include "rcv_internal.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace rcv {
+
+// ---------------------------------------------------------------------------------------
+// resize: per-column / per-row tables built on the host exactly as the oracle does
+// ---------------------------------------------------------------------------------------
+struct ResizeCol {
+  int x0, x1;      // source columns (clamped)
+  int a0, a1;      // u8: 11-bit fixed-point weights
+  float f0, f1;    // f32 weights (1-fx, fx)
+};
+struct ResizeRow {
+  int y0, y1;
+  int b0, b1;
+  float f0, f1;
+};
+
+static void resize_tables(int srows, int scols, int drows, int dcols, std::vector<ResizeCol> &cols,
+                          std::vector<ResizeRow> &rows) {
+  const double scale_x = (double)scols / dcols, scale_y = (double)srows / drows;
+  cols.resize(dcols);
+  rows.resize(drows);
+  for (int dx = 0; dx < dcols; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) {
+      fx = 0.0f;
+      sx = 0;
+    }
+    if (sx >= scols - 1) {
+      fx = 0.0f;
+      sx = scols - 1;
+    }
+    ResizeCol c;
+    c.x0 = sx;
+    c.x1 = sx + 1 < scols ? sx + 1 : sx;
+    c.a0 = (short)lrintf((1.0f - fx) * 2048.0f);
+    c.a1 = (short)lrintf(fx * 2048.0f);
+    c.f0 = 1.0f - fx;
+    c.f1 = fx;
+    cols[dx] = c;
+  }
+  for (int dy = 0; dy < drows; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= (float)sy;
+    ResizeRow r;
+    r.y0 = sy < 0 ? 0 : (sy >= srows ? srows - 1 : sy);
+    r.y1 = sy + 1 < 0 ? 0 : (sy + 1 >= srows ? srows - 1 : sy + 1);
+    r.b0 = (short)lrintf((1.0f - fy) * 2048.0f);
+    r.b1 = (short)lrintf(fy * 2048.0f);
+    r.f0 = 1.0f - fy;
+    r.f1 = fy;
+    rows[dy] = r;
+  }
+}
+
+struct ResizeArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int srows, scols, drows, dcols, cn;
+  const ResizeCol *cols;
+  const ResizeRow *rows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_resize_generic(const ResizeArgs a) {
+  int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  int dy = blockIdx.y;
+  if (dx >= a.dcols) return;
+  const ResizeCol c = a.cols[dx];
+  const ResizeRow r = a.rows[dy];
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const T *s0 = (const T *)(src + (size_t)r.y0 * a.sstep);
+  const T *s1 = (const T *)(src + (size_t)r.y1 * a.sstep);
+  T *d = (T *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep);
+  for (int ch = 0; ch < a.cn; ++ch) {
+    if (sizeof(T) == 1) {
+      int S0 = (int)s0[c.x0 * a.cn + ch] * c.a0 + (int)s0[c.x1 * a.cn + ch] * c.a1;
+      int S1 = (int)s1[c.x0 * a.cn + ch] * c.a0 + (int)s1[c.x1 * a.cn + ch] * c.a1;
+      int v = (((r.b0 * (S0 >> 4)) >> 16) + ((r.b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+      d[dx * a.cn + ch] = (T)min(max(v, 0), 255);
+    } else {
+      float t0 = __fmul_rn((float)s0[c.x0 * a.cn + ch], c.f0);
+      float t1 = __fmul_rn((float)s0[c.x1 * a.cn + ch], c.f1);
+      float h0 = __fadd_rn(t0, t1);
+      float t2 = __fmul_rn((float)s1[c.x0 * a.cn + ch], c.f0);
+      float t3 = __fmul_rn((float)s1[c.x1 * a.cn + ch], c.f1);
+      float h1 = __fadd_rn(t2, t3);
+      d[dx * a.cn + ch] = (T)__fadd_rn(__fmul_rn(h0, r.f0), __fmul_rn(h1, r.f1));
+    }
+  }
+}
+
+// Exact 4x downscale of 3-channel u8 (config 4: 7680x4320 -> 1920x1080).  With scale 4 the
+// oracle's weights are all 1024 and its fixed-point chain collapses to
+//   out = (p[4y+1][4x+1] + p[4y+1][4x+2] + p[4y+2][4x+1] + p[4y+2][4x+2] + 2) >> 2
+// (checked bit-exact against the general model in tests).
+// A thread makes 4 dst pixels: 2 rows x 48 B in (3 x LDG.128 each), 12 B out.
+__device__ __forceinline__ uint32_t byte_at(const uint32_t *w, int k) { return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu; }
+
+__global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 dst pixels
+  int dy = blockIdx.y;
+  int groups = a.dcols >> 2;
+  if (g >= groups) return;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const uint4 *r1 = (const uint4 *)(src + (size_t)(4 * dy + 1) * a.sstep + (size_t)g * 48);
+  const uint4 *r2 = (const uint4 *)(src + (size_t)(4 * dy + 2) * a.sstep + (size_t)g * 48);
+  uint32_t w1[12], w2[12];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    uint4 q = __ldg(r1 + k);
+    w1[4 * k] = q.x;
+    w1[4 * k + 1] = q.y;
+    w1[4 * k + 2] = q.z;
+    w1[4 * k + 3] = q.w;
+    q = __ldg(r2 + k);
+    w2[4 * k] = q.x;
+    w2[4 * k + 1] = q.y;
+    w2[4 * k + 2] = q.z;
+    w2[4 * k + 3] = q.w;
+  }
+  uint32_t out[3] = {0, 0, 0};
+#pragma unroll
+  for (int ob = 0; ob < 12; ++ob) {
+    const int j = ob / 3, ch = ob % 3;
+    const int i0 = 12 * j + 3 + ch, i1 = i0 + 3;
+    uint32_t v = (byte_at(w1, i0) + byte_at(w1, i1) + byte_at(w2, i0) + byte_at(w2, i1) + 2u) >> 2;
+    out[ob >> 2] |= v << ((ob & 3) * 8);
+  }
+  uint32_t *d = (uint32_t *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep + (size_t)g * 12);
+  d[0] = out[0];
+  d[1] = out[1];
+  d[2] = out[2];
+}
+
+int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
+  if (dst.v.rows == 0 || dst.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (src.v.rows == 0 || src.v.cols == 0) return fail(RCV_ERR_SIZE, "resize from an empty image");
+  if (dst.v.rows > 65535 || src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  ResizeArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride,
+               src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, src.v.cn, nullptr, nullptr};
+  const bool al = ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 15) == 0) &&
+                  ((((uintptr_t)dst.v.data | dst.v.step | dst.frame_stride) & 3) == 0);
+  if (src.v.depth == RCV_U8 && src.v.cn == 3 && src.v.rows == 4 * dst.v.rows && src.v.cols == 4 * dst.v.cols &&
+      (dst.v.cols & 3) == 0 && al && opt_get("resize.force_generic", 0) == 0) {
+    dim3 grid(ceil_div(dst.v.cols >> 2, 128), dst.v.rows, src.n);
+    k_resize4x_u8c3<<<grid, 128, 0, s>>>(a);
+    count_launch();
+    RCV_CUDA(cudaGetLastError());
+    return RCV_OK;
+  }
+  std::vector<ResizeCol> cols;
+  std::vector<ResizeRow> rows;
+  resize_tables(src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, cols, rows);
+  void *dcols = nullptr, *drows = nullptr;
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, cols.size() * sizeof(ResizeCol), &dcols));
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_Y, rows.size() * sizeof(ResizeRow), &drows));
+  RCV_CUDA(cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(ResizeCol), cudaMemcpyHostToDevice, s));
+  RCV_CUDA(cudaMemcpyAsync(drows, rows.data(), rows.size() * sizeof(ResizeRow), cudaMemcpyHostToDevice, s));
+  // the vectors die at return: pageable-source async copies are staged before returning,
+  // but make that independent of driver behaviour
+  RCV_CUDA(cudaStreamSynchronize(s));
+  a.cols = (const ResizeCol *)dcols;
+  a.rows = (const ResizeRow *)drows;
+  dim3 grid(ceil_div(dst.v.cols, 256), dst.v.rows, src.n);
+  if (src.v.depth == RCV_U8)
+    k_resize_generic<uint8_t><<<grid, 256, 0, s>>>(a);
+  else
+    k_resize_generic<float><<<grid, 256, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// warpAffine
+// ---------------------------------------------------------------------------------------
+void rotation_matrix(double cx, double cy, double angle_deg, double scale, double M[6]) {
+  double ang = angle_deg * (3.14159265358979323846 / 180.0);
+  double alpha = scale * cos(ang);
+  double beta = scale * sin(ang);
+  M[0] = alpha;
+  M[1] = beta;
+  M[2] = (1 - alpha) * cx - beta * cy;
+  M[3] = -beta;
+  M[4] = alpha;
+  M[5] = beta * cx + (1 - alpha) * cy;
+}
+
+int invert_affine(const double M[6], double iM[6]) {
+  double D = M[0] * M[4] - M[1] * M[3];
+  if (D == 0.0) return -1;
+  D = 1.0 / D;
+  double A11 = M[4] * D, A22 = M[0] * D;
+  double A12 = -M[1] * D, A21 = -M[3] * D;
+  double b1 = -A11 * M[2] - A12 * M[5];
+  double b2 = -A21 * M[2] - A22 * M[5];
+  iM[0] = A11;
+  iM[1] = A12;
+  iM[2] = b1;
+  iM[3] = A21;
+  iM[4] = A22;
+  iM[5] = b2;
+  return 0;
+}
+
+struct WarpArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int srows, scols, drows, dcols, cn;
+  double m1, m2, m4, m5;  // row terms (f64)
+  float m0, m3;           // column factors (f32)
+  float border;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_warp_affine(const WarpArgs a) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.dcols || y >= a.drows) return;
+  // bx = (float)(iM[1]*y + iM[2]) : f64 mul, f64 add, one rounding to f32
+  const float bx = __double2float_rn(__dadd_rn(__dmul_rn(a.m1, (double)y), a.m2));
+  const float by = __double2float_rn(__dadd_rn(__dmul_rn(a.m4, (double)y), a.m5));
+  const float sx = fmaf(a.m0, (float)x, bx);
+  const float sy = fmaf(a.m3, (float)x, by);
+  const float flx = floorf(sx), fly = floorf(sy);
+  const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
+  const bool inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
+  const int ix = inside ? (int)flx : 0, iy = inside ? (int)fly : 0;
+  const bool x0ok = inside && ix >= 0, x1ok = inside && ix + 1 < a.scols;
+  const bool y0ok = inside && iy >= 0, y1ok = inside && iy + 1 < a.srows;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const T *r0 = (const T *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
+  const T *r1 = (const T *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
+  T *d = (T *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)y * a.dstep);
+  for (int ch = 0; ch < a.cn; ++ch) {
+    float p00 = a.border, p01 = a.border, p10 = a.border, p11 = a.border;
+    if (y0ok && x0ok) p00 = (float)__ldg(r0 + ix * a.cn + ch);
+    if (y0ok && x1ok) p01 = (float)__ldg(r0 + (ix + 1) * a.cn + ch);
+    if (y1ok && x0ok) p10 = (float)__ldg(r1 + ix * a.cn + ch);
+    if (y1ok && x1ok) p11 = (float)__ldg(r1 + (ix + 1) * a.cn + ch);
+    float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
+    float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
+    float v = fmaf(fy, __fsub_rn(q1, q0), q0);
+    if (sizeof(T) == 1) {
+      int iv = __float2int_rn(v);
+      d[x * a.cn + ch] = (T)min(max(iv, 0), 255);
+    } else {
+      d[x * a.cn + ch] = (T)v;
+    }
+  }
+}
+
+int launch_warp_affine(Ctx *, const DBatch &src, const DBatch &dst, const double iM[6], double border,
+                       cudaStream_t s) {
+  if (dst.v.rows == 0 || dst.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "batch too large");
+  WarpArgs a;
+  a.src = src.v.data;
+  a.sstep = src.v.step;
+  a.sfs = src.frame_stride;
+  a.dst = dst.v.data;
+  a.dstep = dst.v.step;
+  a.dfs = dst.frame_stride;
+  a.srows = src.v.rows;
+  a.scols = src.v.cols;
+  a.drows = dst.v.rows;
+  a.dcols = dst.v.cols;
+  a.cn = src.v.cn;
+  a.m0 = (float)iM[0];
+  a.m1 = iM[1];
+  a.m2 = iM[2];
+  a.m3 = (float)iM[3];
+  a.m4 = iM[4];
+  a.m5 = iM[5];
+  a.border = src.v.depth == RCV_U8 ? (float)(int)border : (float)border;
+  dim3 block(32, 8, 1);
+  dim3 grid(ceil_div(a.dcols, 32), ceil_div(a.drows, 8), src.n);
+  if (grid.y > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall");
+  if (src.v.depth == RCV_U8)
+    k_warp_affine<uint8_t><<<grid, block, 0, s>>>(a);
+  else
+    k_warp_affine<float><<<grid, block, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+}  // namespace rcv

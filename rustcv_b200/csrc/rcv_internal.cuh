@@ -1,0 +1,139 @@
+// rcv_internal.cuh -- shared declarations of librcv_imgproc.so (not installed).
+//
+// Layout of the library:
+//   context.cu   per-GPU context, streams, staging rings, device Mats, options
+//   tma.cu       cuTensorMapEncodeTiled plumbing (driver entry point, no -lcuda)
+//   cvt.cu       pixel-format conversion kernels     (videoio/mod.rs:344-399)
+//   stencil.cu   TMA strip-pipeline kernels: binomial Gaussian u8, Sobel f32
+//   filter.cu    generic separable / dense filters (u8 Q8, f32)
+//   geom.cu      bilinear resize, warpAffine
+//   abi.cu       the extern "C" entry points of include/rcv_imgproc.h
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <mutex>
+
+#include "../../include/rcv_imgproc.h"
+
+namespace rcv {
+
+// ---- errors ---------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define RCV_CUDA(expr)                                     \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return rcv::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define RCV_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != RCV_OK) return _rc; \
+  } while (0)
+
+// ---- device image view -----------------------------------------------------
+// A Mat whose storage is in HBM.  step in bytes; cn channels; depth RCV_U8/F32.
+struct DView {
+  uint8_t *data;
+  int rows, cols;
+  size_t step;
+  int cn;
+  int depth;
+  __host__ __device__ size_t elem() const { return depth == RCV_F32 ? 4 : 1; }
+  __host__ __device__ size_t row_bytes() const { return (size_t)cols * cn * elem(); }
+};
+
+// n frames of one geometry; frame j = data + j*frame_stride.
+struct DBatch {
+  DView v;              // geometry + frame 0
+  size_t frame_stride;  // bytes between frames (0 when n == 1)
+  int n;
+};
+
+// ---- context ----------------------------------------------------------------
+constexpr int kRing = 4;  // staging ring depth for host-resident batches
+
+enum ScratchSlot {
+  SCR_STAGE_IN0 = 0,   // + slot            (kRing staged inputs; NV12 uses slot 1 for the UV plane)
+  SCR_STAGE_OUT0 = 8,  // + slot*3 + output (kRing x up to 3 staged outputs)
+  SCR_TABLE_X = 24,
+  SCR_TABLE_Y = 25,
+  SCR_TAPS = 26,
+  SCR_FUSE_TMP = 27,  // intermediate BGR of the two-pass YUYV->BGR->Gaussian chain
+  SCR_COUNT = 32
+};
+
+struct Ctx {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;    // kernels (and single-Mat copies)
+  cudaStream_t s_in = nullptr;      // H2D of pipelined host batches
+  cudaStream_t s_out = nullptr;     // D2H of pipelined host batches
+  cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {};
+  void *scratch[SCR_COUNT] = {};
+  size_t scratch_bytes[SCR_COUNT] = {};
+  std::mutex mu;
+};
+
+Ctx *ctx_get(int device);      // NULL (and error set) when not initialised
+Ctx *ctx_default();
+inline cudaStream_t ctx_stream(Ctx *c) { return c->stream; }
+inline int ctx_device(Ctx *c) { return c->device; }
+inline int ctx_sm_count(Ctx *c) { return c->sm_count; }
+bool ctx_blocking();
+void count_launch(int n = 1);
+int64_t opt_get(const char *name, int64_t dflt);
+
+// device scratch that lives as long as the context (grown on demand).
+int ctx_scratch(Ctx *c, int slot, size_t bytes, void **ptr);
+
+// ---- TMA ---------------------------------------------------------------------
+// 3-D tensor map over a batch of strided byte rows viewed as u32 words:
+// dims {ceil(row_bytes/4), rows, n}, strides {step, frame_stride}, box {box_w, box_h, 1}.
+int make_tmap_rows_u32(CUtensorMap *out, const void *base, size_t row_bytes, int rows, size_t step, int n,
+                       size_t frame_stride, int box_w_words, int box_h);
+
+// ---- kernel launchers (device views only; enqueue on `s`) ------------------------
+int launch_cvt(Ctx *c, const DBatch &src, const DBatch &dst, int code, cudaStream_t s);
+int launch_nv12(Ctx *c, const DView &y, const DView &uv, const DView &dst, cudaStream_t s);
+
+int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh, double sx, double sy,
+                    cudaStream_t s);
+int launch_sepfilter_q8(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, int kw,
+                        const int32_t *ky, int kh, cudaStream_t s);
+int launch_sepfilter_f32(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky,
+                         int kh, cudaStream_t s);
+int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                    cudaStream_t s);
+// any of mag/gx/gy may have data == NULL
+int launch_sobel(Ctx *c, const DBatch &src, const DBatch &mag, const DBatch &gx, const DBatch &gy,
+                 cudaStream_t s);
+int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const double iM[6], double border,
+                       cudaStream_t s);
+int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+
+// host-side helpers shared by abi.cu and the launchers (OpenCV models, see oracle/)
+int gaussian_ksize(double sigma, bool is_u8);
+void gaussian_kernel_f64(int n, double sigma, double *kd);
+void gaussian_kernel_q8(int n, double sigma, int32_t *kq);
+void rotation_matrix(double cx, double cy, double angle_deg, double scale, double M[6]);
+int invert_affine(const double M[6], double iM[6]);
+
+// ---- small device helpers ------------------------------------------------------------
+__host__ __device__ inline int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace rcv

@@ -1,0 +1,195 @@
+"""`rustcv::imgproc` on the B200 backend.
+
+Free functions over `Mat` in the style of the reference's only imgproc functions
+(`rectangle(mat, ...)`, rustcv/src/imgproc/drawing.rs:67) with OpenCV argument order:
+`op(src, dst, params...)`.  As `VideoCapture::read` does for its output
+(rustcv/src/videoio/mod.rs:192-199), the wrapper sizes a HOST `dst` before the call;
+device / pinned dsts must already have the right geometry.  Every function forwards to
+one entry point of include/rcv_imgproc.h; errors surface as `RcvError` (the Rust
+wrapper maps the same codes to `anyhow!`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi as F
+from .mat import F32, U8, Mat, MatBatch
+
+COLOR_YUYV2BGR = F.COLOR_YUYV2BGR
+COLOR_UYVY2BGR = F.COLOR_UYVY2BGR
+COLOR_BGRA2BGR = F.COLOR_BGRA2BGR
+COLOR_RGB2BGR = F.COLOR_RGB2BGR
+COLOR_BGR2RGB = F.COLOR_BGR2RGB
+COLOR_BGR2GRAY = F.COLOR_BGR2GRAY
+COLOR_BGR2XRGB32 = F.COLOR_BGR2XRGB32
+COLOR_YUYV2GRAY = F.COLOR_YUYV2GRAY
+
+_DST_CHANNELS = {COLOR_YUYV2BGR: 3, COLOR_UYVY2BGR: 3, COLOR_BGRA2BGR: 3, COLOR_RGB2BGR: 3,
+                 COLOR_BGR2GRAY: 1, COLOR_BGR2XRGB32: 4, COLOR_YUYV2GRAY: 1}
+
+
+def init(device: int = 0) -> None:
+    F.check(F.lib.rcv_init(device))
+
+
+def shutdown() -> None:
+    F.check(F.lib.rcv_shutdown())
+
+
+def _size_dst(dst: Mat, rows: int, cols: int, channels: int, depth: int) -> None:
+    if dst.loc == F.RCV_HOST:
+        dst.ensure_size(rows, cols, channels, depth)
+
+
+def cvt_color(src: Mat, dst: Mat, code: int) -> None:
+    if code not in _DST_CHANNELS:
+        raise F.RcvError(F.RCV_ERR_ARG, f"unknown colour conversion code {code}")
+    _size_dst(dst, src.rows, src.cols, _DST_CHANNELS[code], U8)
+    F.check(F.lib.rcv_cvt_color(C.byref(src.c()), C.byref(dst.c()), code))
+
+
+def yuyv_to_bgr(src: Mat, dst: Mat) -> None:
+    _size_dst(dst, src.rows, src.cols, 3, U8)
+    F.check(F.lib.rcv_yuyv_to_bgr(C.byref(src.c()), C.byref(dst.c())))
+
+
+def nv12_to_bgr(y: Mat, uv: Mat, dst: Mat) -> None:
+    _size_dst(dst, y.rows, y.cols, 3, U8)
+    F.check(F.lib.rcv_nv12_to_bgr(C.byref(y.c()), C.byref(uv.c()), C.byref(dst.c())))
+
+
+def gaussian_blur(src: Mat, dst: Mat, ksize=(5, 5), sigma_x: float = 0.0, sigma_y: float = 0.0) -> None:
+    _size_dst(dst, src.rows, src.cols, src.channels, src.depth)
+    F.check(F.lib.rcv_gaussian_blur(C.byref(src.c()), C.byref(dst.c()), ksize[0], ksize[1], sigma_x, sigma_y))
+
+
+def sep_filter2d(src: Mat, dst: Mat, kx, ky) -> None:
+    """f32 images take f32 taps; u8 images take Q8 integer taps."""
+    _size_dst(dst, src.rows, src.cols, src.channels, src.depth)
+    if src.depth == F32:
+        kx = np.ascontiguousarray(kx, dtype=np.float32)
+        ky = np.ascontiguousarray(ky, dtype=np.float32)
+        F.check(F.lib.rcv_sep_filter2d(C.byref(src.c()), C.byref(dst.c()), kx.ctypes.data_as(C.POINTER(C.c_float)),
+                                       kx.size, ky.ctypes.data_as(C.POINTER(C.c_float)), ky.size))
+    else:
+        kx = np.ascontiguousarray(kx, dtype=np.int32)
+        ky = np.ascontiguousarray(ky, dtype=np.int32)
+        F.check(F.lib.rcv_sep_filter2d_q8(C.byref(src.c()), C.byref(dst.c()), kx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          kx.size, ky.ctypes.data_as(C.POINTER(C.c_int32)), ky.size))
+
+
+def filter2d(src: Mat, dst: Mat, kernel, delta: float = 0.0) -> None:
+    k = np.ascontiguousarray(kernel, dtype=np.float32)
+    assert k.ndim == 2
+    _size_dst(dst, src.rows, src.cols, src.channels, src.depth)
+    F.check(F.lib.rcv_filter2d(C.byref(src.c()), C.byref(dst.c()), k.ctypes.data_as(C.POINTER(C.c_float)),
+                               k.shape[1], k.shape[0], delta))
+
+
+def sobel_mag(src: Mat, mag: Mat | None, gx: Mat | None = None, gy: Mat | None = None) -> None:
+    ptrs = []
+    for o in (mag, gx, gy):
+        if o is None:
+            ptrs.append(None)
+        else:
+            _size_dst(o, src.rows, src.cols, 1, F32)
+            ptrs.append(C.byref(o.c()))
+    F.check(F.lib.rcv_sobel_mag(C.byref(src.c()), *ptrs))
+
+
+def resize(src: Mat, dst: Mat, dsize: tuple[int, int] | None = None) -> None:
+    """cv::resize INTER_LINEAR; dsize = (width, height) as in OpenCV, or dst's own geometry."""
+    if dsize is not None:
+        _size_dst(dst, dsize[1], dsize[0], src.channels, src.depth)
+    F.check(F.lib.rcv_resize_bilinear(C.byref(src.c()), C.byref(dst.c())))
+
+
+def get_rotation_matrix_2d(center: tuple[float, float], angle_deg: float, scale: float = 1.0) -> np.ndarray:
+    m = (C.c_double * 6)()
+    F.check(F.lib.rcv_get_rotation_matrix_2d(center[0], center[1], angle_deg, scale, m))
+    return np.array(m[:], dtype=np.float64).reshape(2, 3)
+
+
+def warp_affine(src: Mat, dst: Mat, M, dsize: tuple[int, int] | None = None, inverse_map: bool = False,
+                border_value: float = 0.0) -> None:
+    m = (C.c_double * 6)(*[float(v) for v in np.asarray(M, dtype=np.float64).ravel()])
+    if dsize is None:
+        dsize = (src.cols, src.rows)
+    _size_dst(dst, dsize[1], dsize[0], src.channels, src.depth)
+    F.check(F.lib.rcv_warp_affine(C.byref(src.c()), C.byref(dst.c()), m, int(inverse_map), border_value))
+
+
+def yuyv_to_bgr_gaussian5(src: Mat, dst: Mat) -> None:
+    _size_dst(dst, src.rows, src.cols, 3, U8)
+    F.check(F.lib.rcv_yuyv_to_bgr_gaussian5(C.byref(src.c()), C.byref(dst.c())))
+
+
+# ---- batches of independent frames -------------------------------------------------------
+def _arr(b) -> tuple:
+    if isinstance(b, MatBatch):
+        return b.arr, b.n
+    mb = MatBatch.of(list(b))
+    return mb.arr, mb.n
+
+
+def gaussian_blur_batch(srcs, dsts, ksize=(5, 5), sigma_x: float = 0.0, sigma_y: float = 0.0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_gaussian_blur_batch(sa, da, n, ksize[0], ksize[1], sigma_x, sigma_y))
+
+
+def sobel_mag_batch(srcs, mags) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(mags)
+    assert n == m
+    F.check(F.lib.rcv_sobel_mag_batch(sa, da, n))
+
+
+def resize_batch(srcs, dsts) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_resize_bilinear_batch(sa, da, n))
+
+
+def warp_affine_batch(srcs, dsts, M, inverse_map: bool = False, border_value: float = 0.0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    mm = (C.c_double * 6)(*[float(v) for v in np.asarray(M, dtype=np.float64).ravel()])
+    F.check(F.lib.rcv_warp_affine_batch(sa, da, n, mm, int(inverse_map), border_value))
+
+
+def cvt_color_batch(srcs, dsts, code: int) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_cvt_color_batch(sa, da, n, code))
+
+
+# ---- runtime knobs ---------------------------------------------------------------------------
+def set_option(name: str, value: int) -> None:
+    F.check(F.lib.rcv_set_option(name.encode(), value))
+
+
+def set_blocking(blocking: bool) -> None:
+    F.check(F.lib.rcv_set_blocking(int(blocking)))
+
+
+def sync(device: int = -1) -> None:
+    F.check(F.lib.rcv_sync(device))
+
+
+def launch_count() -> int:
+    n = C.c_uint64()
+    F.check(F.lib.rcv_launch_count(C.byref(n)))
+    return n.value
+
+
+def stream_ptr(device: int = -1) -> int:
+    p = C.c_void_p()
+    F.check(F.lib.rcv_get_stream(device, C.byref(p)))
+    return p.value or 0

@@ -1,0 +1,219 @@
+"""CPU suite, part 1: pins the oracle.
+
+(a) the reference's own unit tests for the pixel path (rustcv-camera/src/decode.rs:234-273),
+(b) hand-derived known answers and SplitMix64 frame CRCs from SURVEY.md section 8c/8d,
+(c) OpenCV 4.13 outputs (tests/golden/cv2_golden.npz) for the ops the reference lacks,
+(d) an independent numpy restatement of the BT.601 formula over the whole (Y,U,V) domain.
+"""
+import numpy as np
+import pytest
+
+
+# ---- (a) reference unit tests --------------------------------------------------------
+def test_ref_yuyv_to_bgr_basic(oracle):
+    # decode.rs:235-252: Y=235, U=V=128 -> every channel > 240 (exactly 255)
+    src = np.array([235, 128, 235, 128], np.uint8)
+    for fn in (oracle.yuyv_to_bgr_facade, oracle.yuyv_to_bgr_camera):
+        st, dst = fn(src, 2, 1)
+        assert st == 0 and (dst > 240).all() and (dst == 255).all()
+
+
+def test_ref_yuyv_to_bgr_black(oracle):
+    # decode.rs:255-265: Y=16 -> every channel < 10 (exactly 0)
+    src = np.array([16, 128, 16, 128], np.uint8)
+    st, dst = oracle.yuyv_to_bgr_camera(src, 2, 1)
+    assert st == 0 and (dst < 10).all() and (dst == 0).all()
+
+
+def test_ref_rgb_to_bgr_swap(oracle):
+    # decode.rs:268-273
+    src = np.array([255, 0, 0, 0, 255, 0], np.uint8).reshape(1, 2, 3)
+    assert oracle.swap_rb(src).ravel().tolist() == [0, 0, 255, 0, 255, 0]
+
+
+# ---- (b) known answers / goldens ---------------------------------------------------------
+def test_splitmix64_check_value(oracle):
+    assert int(oracle.splitmix64(0, 1)[0]) == 0xE220A8397B1DCDAF
+    # C and numpy generators agree
+    import ctypes as C
+    buf = np.zeros(1001, np.uint8)
+    oracle.lib().orc_fill_u8(C.c_uint64(5), C.c_void_p(buf.ctypes.data), C.c_size_t(buf.size))
+    assert (buf == oracle.fill_u8(5, 1001)).all()
+    fb = np.zeros(77, np.float32)
+    oracle.lib().orc_fill_f32(C.c_uint64(6), C.c_void_p(fb.ctypes.data), C.c_size_t(fb.size))
+    assert (fb == oracle.fill_f32(6, 77)).all()
+
+
+def test_yuyv_known_answers(oracle):
+    st, d = oracle.yuyv_to_bgr_facade(np.full(4, 255, np.uint8), 2, 1)
+    assert d.tolist() == [255, 125, 255, 255, 125, 255]
+    st, d = oracle.yuyv_to_bgr_facade(np.zeros(4, np.uint8), 2, 1)
+    assert d.tolist() == [0, 135, 0, 0, 135, 0]
+
+
+def test_yuyv_cfg1_golden(oracle):
+    src = oracle.fill_u8(1, 640 * 480 * 2)
+    assert oracle.crc32(src) == 0x08EB63F6
+    st, dst = oracle.yuyv_to_bgr_facade(src, 640, 480)
+    assert st == 0 and oracle.crc32(dst) == 0x0BF66518
+    assert dst[:6].tolist() == [133, 213, 220, 0, 0, 0]
+    # strided form == packed form on an even-width frame
+    assert (oracle.yuyv_to_bgr(src.reshape(480, 640, 2)).ravel() == dst).all()
+
+
+def test_yuyv_contract_edges(oracle):
+    src = oracle.fill_u8(3, 6 * 4 * 2)
+    # facade: short src -> silent return (1); short dst -> would panic (-1)
+    assert oracle.yuyv_to_bgr_facade(src[:-1], 6, 4)[0] == 1
+    assert oracle.yuyv_to_bgr_facade(src, 6, 4, dst_len=6 * 4 * 3 - 1)[0] == -1
+    # camera crate checks both
+    assert oracle.yuyv_to_bgr_camera(src, 6, 4, dst_len=6 * 4 * 3 - 1)[0] == 1
+    # odd pixel count: last pixel dropped (w*h/2 iterations)
+    st, d = oracle.yuyv_to_bgr_facade(oracle.fill_u8(3, 3 * 3 * 2), 3, 3)
+    assert st == 0 and (d[24:] == 0).all()
+
+
+def test_yuv_formula_exhaustive(oracle):
+    """All 2^24 (Y,U,V): C oracle == an independent numpy statement of videoio/mod.rs:352-369."""
+    u, v = np.meshgrid(np.arange(256, dtype=np.int32), np.arange(256, dtype=np.int32), indexing="ij")
+    u = u.ravel()
+    v = v.ravel()
+    for y in range(0, 256):
+        frame = np.empty((65536, 4), np.uint8)
+        frame[:, 0] = y
+        frame[:, 1] = u
+        frame[:, 2] = 255 - y
+        frame[:, 3] = v
+        st, got = oracle.yuyv_to_bgr_facade(frame.ravel(), 65536 * 2, 1)
+        got = got.reshape(65536, 6)
+        for k, yy in ((0, y), (3, 255 - y)):
+            c = yy - 16
+            b = np.clip((298 * c + 516 * (u - 128) + 128) >> 8, 0, 255)
+            g = np.clip((298 * c - 100 * (u - 128) - 208 * (v - 128) + 128) >> 8, 0, 255)
+            r = np.clip((298 * c + 409 * (v - 128) + 128) >> 8, 0, 255)
+            assert (got[:, k] == b).all() and (got[:, k + 1] == g).all() and (got[:, k + 2] == r).all()
+
+
+def test_gauss_cfg2_golden(oracle):
+    oracle.set_threads(8)
+    img = oracle.fill_u8(2, 2160 * 3840 * 3).reshape(2160, 3840, 3)
+    assert oracle.crc32(img) == 0xD15B0894
+    g = oracle.gaussian_blur(img, (5, 5))
+    oracle.set_threads(1)
+    assert oracle.crc32(g) == 0x827081C8
+    assert g[0, 0].tolist() == [123, 104, 111] and g[1079, 1919].tolist() == [97, 153, 135]
+
+
+def test_sobel_cfg3_input_golden(oracle):
+    f = oracle.fill_f32(3, 1080 * 1920)
+    assert oracle.crc32(f) == 0xA837E897
+    assert np.allclose(f[:3], [0.85549253, 0.11345029, 0.4824472], rtol=0, atol=1e-8)
+
+
+def test_resize_cfg4_golden(oracle):
+    oracle.set_threads(8)
+    s = oracle.fill_u8(4, 4320 * 7680 * 3).reshape(4320, 7680, 3)
+    assert oracle.crc32(s) == 0xC7614ADC
+    r = oracle.resize_bilinear(s, 1080, 1920)
+    oracle.set_threads(1)
+    assert oracle.crc32(r) == 0x31A84A85
+    # exact-4x closed form
+    a = s[1::4, 1::4].astype(np.int32) + s[1::4, 2::4] + s[2::4, 1::4] + s[2::4, 2::4]
+    assert (((a + 2) >> 2).astype(np.uint8) == r).all()
+
+
+def test_threads_do_not_change_results(oracle):
+    img = oracle.fill_u8(12, 97 * 131 * 3).reshape(97, 131, 3)
+    a = oracle.gaussian_blur(img, (7, 7), 1.3)
+    oracle.set_threads(5)
+    b = oracle.gaussian_blur(img, (7, 7), 1.3)
+    oracle.set_threads(1)
+    assert (a == b).all()
+
+
+# ---- (c) OpenCV pins -------------------------------------------------------------------------
+def _inputs(oracle, golden):
+    H, W = [int(x) for x in golden["shape"]]
+    return (oracle.fill_u8(7, H * W * 3).reshape(H, W, 3), oracle.fill_u8(8, H * W).reshape(H, W),
+            oracle.fill_f32(9, H * W).reshape(H, W), oracle.fill_u8(10, H * W * 4).reshape(H, W, 4))
+
+
+def test_cv2_gaussian_bit_exact(oracle, golden):
+    bgr, gray, _, bgra = _inputs(oracle, golden)
+    for key in golden.files:
+        if not key.startswith("gauss_bgr_"):
+            continue
+        kw, kh, sg = key[len("gauss_bgr_"):].split("_")
+        got = oracle.gaussian_blur(bgr, (int(kw), int(kh)), float(sg), float(sg))
+        assert (got == golden[key]).all(), key
+    assert (oracle.gaussian_blur(gray, (5, 5)) == golden["gauss_gray_5_5_0"]).all()
+    assert (oracle.gaussian_blur(bgra, (5, 5)) == golden["gauss_bgra_5_5_0"]).all()
+
+
+def test_cv2_gray_resize_bit_exact(oracle, golden):
+    bgr, _, _, _ = _inputs(oracle, golden)
+    assert (oracle.bgr_to_gray(bgr) == golden["bgr2gray"]).all()
+    for key in golden.files:
+        if key.startswith("resize_bgr_"):
+            dr, dc = [int(x) for x in key[len("resize_bgr_"):].split("_")]
+            assert (oracle.resize_bilinear(bgr, dr, dc) == golden[key]).all(), key
+    big = oracle.fill_u8(11, 64 * 96 * 3).reshape(64, 96, 3)
+    assert (oracle.resize_bilinear(big, 16, 24) == golden["resize4x_bgr"]).all()
+
+
+def test_cv2_f32_within_tolerance(oracle, golden):
+    _, _, f, _ = _inputs(oracle, golden)
+    s = oracle.sobel3(f, ("gx", "gy", "mag"))
+    assert np.abs(s["gx"] - golden["sobel_gx"]).max() < 2e-6
+    assert np.abs(s["gy"] - golden["sobel_gy"]).max() < 2e-6
+    assert np.abs(s["mag"] - golden["sobel_mag"]).max() < 4e-6
+    H, W = f.shape
+    M = oracle.rotation_matrix((W - 1) / 2, (H - 1) / 2, 15.0)
+    assert np.abs(M.reshape(2, 3) - golden["rotM"]).max() < 1e-12
+    w = oracle.warp_affine(f, M)
+    # OpenCV quantises source coordinates to 1/32 px: loose sanity check only
+    assert np.abs(w - golden["warp_f32"]).max() < 0.05 and np.abs(w - golden["warp_f32"]).mean() < 0.01
+    assert np.abs(oracle.resize_bilinear(f, 30, 41) - golden["resize_f32_30_41"]).max() < 1e-5
+    assert np.abs(oracle.gaussian_blur(f, (5, 5), 1.1, 1.1) - golden["gauss_f32_5_5_1.1"]).max() < 1e-6
+    lap = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
+    assert np.abs(oracle.filter2d(f, lap) - golden["filter2d_f32_lap"]).max() < 1e-5
+
+
+def test_cv2_filter2d_u8(oracle, golden):
+    bgr, _, _, _ = _inputs(oracle, golden)
+    lap = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
+    assert (oracle.filter2d(bgr, lap / 3 + 0.2) == golden["filter2d_bgr"]).all()
+
+
+# ---- (d) strides and degenerate shapes ------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 5), (5, 3)])
+def test_tiny_images_reflect101(oracle, shape):
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+    got = oracle.gaussian_blur(img, (5, 5))
+    # brute force with numpy pad(mode="reflect") semantics generalised to len < radius
+    def refl(p, n):
+        if n == 1:
+            return 0
+        while p < 0 or p >= n:
+            p = -p if p < 0 else 2 * (n - 1) - p
+        return p
+    k = np.array([1, 4, 6, 4, 1])
+    H, W = shape
+    want = np.zeros_like(img)
+    for y in range(H):
+        for x in range(W):
+            acc = np.zeros(3, np.int64)
+            for i in range(5):
+                for j in range(5):
+                    acc += k[i] * k[j] * img[refl(y + i - 2, H), refl(x + j - 2, W)].astype(np.int64)
+            want[y, x] = (acc + 128) >> 8
+    assert (got == want).all()
+
+
+def test_strided_inputs_equal_packed(oracle):
+    img = oracle.fill_u8(13, 33 * 47 * 3).reshape(33, 47, 3)
+    p = oracle.padded(img, 256)
+    assert (oracle.gaussian_blur(p, (5, 5)) == oracle.gaussian_blur(img, (5, 5))).all()
+    assert (oracle.bgr_to_gray(p) == oracle.bgr_to_gray(img)).all()
+    assert (oracle.resize_bilinear(p, 20, 31) == oracle.resize_bilinear(img, 20, 31)).all()

@@ -1,0 +1,595 @@
+"""GPU suite: parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact for every u8 op; f32 ops are bit-exact too where the oracle fixes the
+operation order (Sobel, resize, warpAffine, separable/dense filters), with the 1-ULP
+tolerance BASELINE.json's north_star allows stated in `assert_f32`.
+Sizes are chosen so the oracle finishes in seconds; the full BASELINE.json sizes are
+covered by CRC goldens and size-independent properties at the end.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- helpers --------------------------------------------------------------------------
+def assert_same(got, want, name):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    bad = got != want
+    if bad.ndim == 3:
+        bad2 = bad.any(axis=2)
+    else:
+        bad2 = bad
+    if bad.any():
+        ys, xs = np.nonzero(bad2)
+        first = [(int(y), int(x), got[y, x].tolist(), want[y, x].tolist()) for y, x in list(zip(ys, xs))[:6]]
+        raise AssertionError(
+            f"{name}: {int(bad.sum())} of {bad.size} elements differ; rows {ys.min()}..{ys.max()} "
+            f"cols {xs.min()}..{xs.max()}; distinct rows {len(set(ys.tolist()))} distinct cols {len(set(xs.tolist()))}; "
+            f"first (y, x, got, want): {first}")
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return np.abs(a - b)
+
+
+def assert_f32(got, want, name, max_ulp=1):
+    """north_star tolerance: within 1 ULP for f32."""
+    d = ulp_diff(got, want)
+    if d.max() > max_ulp:
+        ys, xs = np.nonzero(d > max_ulp)
+        first = [(int(y), int(x), float(got[y, x]), float(want[y, x])) for y, x in list(zip(ys, xs))[:6]]
+        raise AssertionError(f"{name}: max ulp {int(d.max())}, {int((d > max_ulp).sum())} elements beyond {max_ulp} ulp; "
+                             f"rows {ys.min()}..{ys.max()} cols {xs.min()}..{xs.max()}; first {first}")
+
+
+def mats(R, a, where, step=None):
+    """A Mat holding `a` as host (packed or padded), pinned or device storage."""
+    if where == "host":
+        return R.Mat.from_numpy(a) if step is None else R.Mat.from_numpy_strided(a, step)
+    if where == "pinned":
+        cn = 1 if a.ndim == 2 else a.shape[2]
+        m = R.Mat.pinned(a.shape[0], a.shape[1], cn, R.F32 if a.dtype == np.float32 else R.U8)
+        m.data[:] = np.ascontiguousarray(a).view(np.uint8).ravel()
+        return m
+    return R.Mat.from_numpy(a).upload()
+
+
+def out_like(R, src, where, channels=None, depth=None, rows=None, cols=None):
+    if where == "host":
+        return R.Mat.empty()
+    return src.like(channels=channels, depth=depth, rows=rows, cols=cols)
+
+
+WHERE = ["host", "device", "pinned"]
+
+
+# ---- conversions (the reference's real loops) ----------------------------------------------
+def test_reference_unit_tests_on_gpu(rcv):
+    R = rcv
+    # rustcv-camera/src/decode.rs:235-273 run against the CUDA path
+    d = R.Mat.empty()
+    R.imgproc.yuyv_to_bgr(R.Mat.from_numpy(np.array([[[235, 128], [235, 128]]], np.uint8)), d)
+    assert (d.to_numpy() > 240).all() and (d.to_numpy() == 255).all()
+    R.imgproc.yuyv_to_bgr(R.Mat.from_numpy(np.array([[[16, 128], [16, 128]]], np.uint8)), d)
+    assert (d.to_numpy() < 10).all()
+    R.imgproc.cvt_color(R.Mat.from_numpy(np.array([[[255, 0, 0], [0, 255, 0]]], np.uint8)), d, R.imgproc.COLOR_RGB2BGR)
+    assert d.to_numpy().ravel().tolist() == [0, 0, 255, 0, 255, 0]
+
+
+def test_yuyv_cfg1_packed_facade_contract(rcv, oracle):
+    """BASELINE.json config 1: one 640x480 YUYV frame into a Mat, facade contract."""
+    R = rcv
+    src = oracle.fill_u8(1, 640 * 480 * 2)
+    m = R.Mat.empty()
+    assert R.videoio.decode_frame(src, 640, 480, R.videoio.YUYV, m)
+    assert (m.rows, m.cols, m.channels, m.step) == (480, 640, 3, 1920)
+    assert oracle.crc32(m.data) == 0x0BF66518
+    assert m.data[:6].tolist() == [133, 213, 220, 0, 0, 0]
+    # odd pixel count: w*h/2 macro-pixels as one packed run, last pixel untouched
+    src = oracle.fill_u8(3, 5 * 3 * 2)
+    m = R.Mat.empty()
+    R.videoio.decode_frame(src, 5, 3, R.videoio.YUYV, m)
+    st, want = oracle.yuyv_to_bgr_facade(src, 5, 3)
+    assert st == 0 and (m.data == want).all()
+    # BGRA packed (videoio/mod.rs:385-399)
+    src = oracle.fill_u8(4, 33 * 7 * 4)
+    R.videoio.decode_frame(src, 33, 7, R.videoio.BGRA, m)
+    assert (m.data == oracle.bgra_to_bgr_facade(src, 33, 7)[1]).all()
+
+
+@pytest.mark.parametrize("where", WHERE)
+@pytest.mark.parametrize("shape", [(480, 640), (7, 2), (5, 37), (64, 1024), (3, 1)])
+def test_yuv422_strided(rcv, oracle, where, shape):
+    R = rcv
+    h, w = shape
+    src = oracle.fill_u8(21, h * w * 2).reshape(h, w, 2)
+    for code, fn in ((R.imgproc.COLOR_YUYV2BGR, oracle.yuyv_to_bgr), (R.imgproc.COLOR_UYVY2BGR, oracle.uyvy_to_bgr),
+                     (R.imgproc.COLOR_YUYV2GRAY, oracle.yuyv_to_gray)):
+        s = mats(R, src, where)
+        d = out_like(R, s, where, channels=1 if code == R.imgproc.COLOR_YUYV2GRAY else 3)
+        R.imgproc.cvt_color(s, d, code)
+        assert_same(d.to_numpy(), fn(src), f"cvt {code} {shape} {where}")
+
+
+def test_yuv_formula_exhaustive_on_gpu(rcv):
+    """All 2^24 (Y,U,V) triples through the CUDA kernel vs numpy (videoio/mod.rs:352-369)."""
+    R = rcv
+    u, v = np.meshgrid(np.arange(256, dtype=np.int32), np.arange(256, dtype=np.int32), indexing="ij")
+    u, v = u.ravel(), v.ravel()
+    frame = np.empty((256, 65536, 4), np.uint8)
+    for y in range(256):
+        frame[y, :, 0] = y
+        frame[y, :, 2] = 255 - y
+    frame[:, :, 1] = u[None, :]
+    frame[:, :, 3] = v[None, :]
+    d = R.Mat.empty()
+    R.imgproc.yuyv_to_bgr(R.Mat.from_numpy(frame.reshape(256, 65536 * 2, 2)), d)
+    got = d.to_numpy().reshape(256, 65536, 6)
+    for y in (0, 1, 15, 16, 17, 100, 128, 200, 234, 235, 236, 254, 255):
+        for k, yy in ((0, y), (3, 255 - y)):
+            c = yy - 16
+            b = np.clip((298 * c + 516 * (u - 128) + 128) >> 8, 0, 255)
+            g = np.clip((298 * c - 100 * (u - 128) - 208 * (v - 128) + 128) >> 8, 0, 255)
+            r = np.clip((298 * c + 409 * (v - 128) + 128) >> 8, 0, 255)
+            assert (got[y, :, k] == b).all() and (got[y, :, k + 1] == g).all() and (got[y, :, k + 2] == r).all(), y
+    # every row against the vectorised formula via a checksum of all 2^24 x 2 pixels
+    c0 = frame[:, :, 0].astype(np.int32) - 16
+    uu, vv = frame[:, :, 1].astype(np.int32) - 128, frame[:, :, 3].astype(np.int32) - 128
+    assert (got[:, :, 0] == np.clip((298 * c0 + 516 * uu + 128) >> 8, 0, 255)).all()
+    assert (got[:, :, 1] == np.clip((298 * c0 - 100 * uu - 208 * vv + 128) >> 8, 0, 255)).all()
+    assert (got[:, :, 2] == np.clip((298 * c0 + 409 * vv + 128) >> 8, 0, 255)).all()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("shape", [(31, 45), (16, 64), (1, 1), (9, 257)])
+def test_byte_format_conversions(rcv, oracle, where, shape):
+    R = rcv
+    h, w = shape
+    bgr = oracle.fill_u8(22, h * w * 3).reshape(h, w, 3)
+    bgra = oracle.fill_u8(23, h * w * 4).reshape(h, w, 4)
+    I = R.imgproc
+    for code, src, fn, cn in ((I.COLOR_BGRA2BGR, bgra, oracle.bgra_to_bgr, 3), (I.COLOR_RGB2BGR, bgr, oracle.swap_rb, 3),
+                              (I.COLOR_BGR2GRAY, bgr, oracle.bgr_to_gray, 1), (I.COLOR_BGR2XRGB32, bgr, None, 4)):
+        s = mats(R, src, where)
+        d = out_like(R, s, where, channels=cn)
+        I.cvt_color(s, d, code)
+        if fn is None:
+            want = oracle.bgr_to_xrgb32(bgr).view(np.uint8).reshape(h, w, 4)
+        else:
+            want = fn(src)
+        assert_same(d.to_numpy(), want, f"cvt {code} {shape} {where}")
+    # padded steps (Mat.step > cols*channels), unaligned -> scalar kernels
+    s = R.Mat.from_numpy_strided(bgr, step=w * 3 + 5)
+    d = R.Mat.empty()
+    I.cvt_color(s, d, I.COLOR_BGR2GRAY)
+    assert_same(d.to_numpy(), oracle.bgr_to_gray(bgr), "gray strided")
+
+
+def test_nv12(rcv, oracle):
+    R = rcv
+    h, w = 34, 58
+    y = oracle.fill_u8(24, h * w).reshape(h, w)
+    uv = oracle.fill_u8(25, (h // 2) * (w // 2) * 2).reshape(h // 2, w // 2, 2)
+    d = R.Mat.empty()
+    R.imgproc.nv12_to_bgr(R.Mat.from_numpy(y), R.Mat.from_numpy(uv), d)
+    assert_same(d.to_numpy(), oracle.nv12_to_bgr(y, uv.reshape(h // 2, w)), "nv12")
+
+
+# ---- GaussianBlur ---------------------------------------------------------------------------
+GAUSS_SHAPES = [(61, 83, 3), (8, 8, 3), (64, 160, 3), (97, 161, 3), (300, 500, 3), (40, 1000, 3), (500, 24, 3),
+                (33, 160, 1), (50, 481, 1), (45, 70, 2), (61, 83, 4), (72, 120, 4), (250, 321, 3)]
+
+
+@pytest.mark.parametrize("where", WHERE)
+@pytest.mark.parametrize("shape", GAUSS_SHAPES)
+def test_gaussian5_binomial_strip_kernel(rcv, oracle, where, shape):
+    """The metric kernel (k_strip<Gauss5Op>): every edge combination vs the oracle."""
+    R = rcv
+    h, w, cn = shape
+    a = oracle.fill_u8(30 + h + w, h * w * cn).reshape(h, w, cn)
+    if cn == 1:
+        a = a.reshape(h, w)
+    s = mats(R, a, where)
+    d = out_like(R, s, where)
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), f"gauss5 {shape} {where}")
+
+
+@pytest.mark.parametrize("band_rows", [8, 12, 28, 36, 100])
+def test_gaussian5_band_seams(rcv, oracle, band_rows):
+    """Band boundaries (warm-up rows) and multi-chunk pipelines must be seamless."""
+    R = rcv
+    a = oracle.fill_u8(41, 211 * 1003 * 3).reshape(211, 1003, 3)
+    R.imgproc.set_option("gauss.band_rows", band_rows)
+    try:
+        s = mats(R, a, "device")
+        d = s.like()
+        R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+        assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), f"band_rows {band_rows}")
+    finally:
+        R.imgproc.set_option("gauss.band_rows", 0)
+
+
+def test_gaussian5_generic_kernel_agrees(rcv, oracle):
+    R = rcv
+    a = oracle.fill_u8(42, 97 * 161 * 3).reshape(97, 161, 3)
+    R.imgproc.set_option("gauss.force_generic", 1)
+    try:
+        d = R.Mat.empty()
+        R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, (5, 5), 0.0)
+        assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), "generic 5x5")
+    finally:
+        R.imgproc.set_option("gauss.force_generic", 0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3), (1, 9, 3), (9, 1, 3), (2, 2, 1), (3, 5, 3), (5, 3, 4), (7, 300, 3), (300, 7, 3)])
+def test_gaussian_tiny_images(rcv, oracle, shape):
+    R = rcv
+    h, w, cn = shape
+    a = oracle.fill_u8(43, h * w * cn).reshape(h, w, cn)
+    if cn == 1:
+        a = a.reshape(h, w)
+    for ks in ((5, 5), (3, 3)):
+        d = R.Mat.empty()
+        R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, ks, 0.0)
+        assert_same(d.to_numpy(), oracle.gaussian_blur(a, ks), f"tiny {shape} {ks}")
+
+
+@pytest.mark.parametrize("ks,sigma", [((3, 3), 0), ((7, 7), 0), ((5, 5), 1.0), ((7, 7), 1.5), ((9, 9), 2.0), ((0, 0), 1.2),
+                                      ((5, 3), 0.8), ((11, 11), 0), ((31, 31), 5.0)])
+def test_gaussian_general_taps_u8(rcv, oracle, ks, sigma):
+    R = rcv
+    a = oracle.fill_u8(44, 61 * 83 * 3).reshape(61, 83, 3)
+    d = R.Mat.empty()
+    R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, ks, float(sigma))
+    assert_same(d.to_numpy(), oracle.gaussian_blur(a, ks, float(sigma), float(sigma)), f"gauss {ks} {sigma}")
+
+
+def test_gaussian_strided_and_padding_untouched(rcv, oracle):
+    """Mat.step > cols*channels on input AND output; padding bytes must survive."""
+    R = rcv
+    a = oracle.fill_u8(45, 70 * 90 * 3).reshape(70, 90, 3)
+    s = R.Mat.from_numpy_strided(a, step=90 * 3 + 50)
+    d = R.Mat.from_numpy_strided(np.zeros_like(a), step=90 * 3 + 13, fill=0x5A)
+    # a strided host dst is used as it is when it already has the right geometry
+    from rustcv_b200 import _ffi as F
+    F.check(F.lib.rcv_gaussian_blur(C.byref(s.c()), C.byref(d.c()), 5, 5, 0.0, 0.0))
+    assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), "strided")
+    assert (d.data.reshape(70, d.step)[:, 270:] == 0x5A).all()
+
+
+def test_gaussian_golden_fixtures(rcv, oracle, golden):
+    """OpenCV 4.13 outputs committed under tests/golden/ (bit-exact)."""
+    R = rcv
+    H, W = [int(x) for x in golden["shape"]]
+    bgr = oracle.fill_u8(7, H * W * 3).reshape(H, W, 3)
+    for key in golden.files:
+        if key.startswith("gauss_bgr_"):
+            kw, kh, sg = key[len("gauss_bgr_"):].split("_")
+            for where in ("host", "device"):
+                s = mats(R, bgr, where)
+                d = out_like(R, s, where)
+                R.imgproc.gaussian_blur(s, d, (int(kw), int(kh)), float(sg))
+                assert_same(d.to_numpy(), golden[key], f"{key} {where}")
+    gray = oracle.fill_u8(8, H * W).reshape(H, W)
+    bgra = oracle.fill_u8(10, H * W * 4).reshape(H, W, 4)
+    for a, key in ((gray, "gauss_gray_5_5_0"), (bgra, "gauss_bgra_5_5_0")):
+        s = mats(R, a, "device")
+        d = s.like()
+        R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+        assert_same(d.to_numpy(), golden[key], key)
+
+
+def test_gaussian_f32(rcv, oracle):
+    R = rcv
+    for cn in (1, 3):
+        a = oracle.fill_f32(46, 61 * 83 * cn).reshape((61, 83) if cn == 1 else (61, 83, cn))
+        for ks, sg in (((5, 5), 1.1), ((3, 3), 0.0), ((9, 7), 2.0)):
+            d = R.Mat.empty()
+            R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, ks, sg)
+            want = oracle.gaussian_blur(a, ks, sg, sg)
+            got = d.to_numpy()
+            assert_f32(got.reshape(61, -1), want.reshape(61, -1), f"gauss f32 {ks} {sg} cn{cn}", max_ulp=0)
+
+
+# ---- separable / dense filters -----------------------------------------------------------------
+def test_sep_filter2d(rcv, oracle):
+    R = rcv
+    a = oracle.fill_f32(47, 50 * 77).reshape(50, 77)
+    kx = np.array([0.25, 0.5, 0.25], np.float32)
+    ky = np.array([-1, 0, 1, 2, 0.5], np.float32)
+    d = R.Mat.empty()
+    R.imgproc.sep_filter2d(R.Mat.from_numpy(a), d, kx, ky)
+    assert_f32(d.to_numpy(), oracle.sepfilter_f32(a, kx, ky), "sepfilter f32", max_ulp=0)
+    u = oracle.fill_u8(48, 50 * 77 * 3).reshape(50, 77, 3)
+    qx = np.array([10, 50, 136, 50, 10], np.int32)
+    qy = np.array([64, 128, 64], np.int32)
+    R.imgproc.sep_filter2d(R.Mat.from_numpy(u), d, qx, qy)
+    assert_same(d.to_numpy(), oracle.sepfilter_u8_q8(u, qx, qy), "sepfilter q8")
+
+
+@pytest.mark.parametrize("ksz", [(3, 3), (5, 5), (7, 3), (4, 4), (1, 1), (9, 9)])
+def test_filter2d(rcv, oracle, ksz):
+    R = rcv
+    rng = np.random.default_rng(5)
+    k = rng.normal(size=ksz).astype(np.float32)
+    a = oracle.fill_f32(49, 45 * 67).reshape(45, 67)
+    d = R.Mat.empty()
+    R.imgproc.filter2d(R.Mat.from_numpy(a), d, k, delta=0.125)
+    assert_f32(d.to_numpy(), oracle.filter2d(a, k, 0.125), f"filter2d f32 {ksz}", max_ulp=0)
+    u = oracle.fill_u8(50, 45 * 67 * 3).reshape(45, 67, 3)
+    ku = (k / max(1e-3, np.abs(k).sum())).astype(np.float32)
+    R.imgproc.filter2d(R.Mat.from_numpy(u), d, ku, delta=3.0)
+    assert_same(d.to_numpy(), oracle.filter2d(u, ku, 3.0), f"filter2d u8 {ksz}")
+
+
+def test_filter2d_golden(rcv, oracle, golden):
+    R = rcv
+    H, W = [int(x) for x in golden["shape"]]
+    bgr = oracle.fill_u8(7, H * W * 3).reshape(H, W, 3)
+    lap = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
+    d = R.Mat.empty()
+    R.imgproc.filter2d(R.Mat.from_numpy(bgr), d, lap / 3 + 0.2)
+    assert_same(d.to_numpy(), golden["filter2d_bgr"], "filter2d cv2 golden")
+
+
+# ---- Sobel + magnitude ----------------------------------------------------------------------------
+@pytest.mark.parametrize("where", WHERE)
+@pytest.mark.parametrize("shape", [(61, 83), (8, 8), (64, 120), (97, 121), (200, 500), (30, 1000), (1, 1), (1, 7), (7, 1),
+                                   (5, 300), (300, 5)])
+def test_sobel_magnitude(rcv, oracle, where, shape):
+    R = rcv
+    h, w = shape
+    a = oracle.fill_f32(51 + h, h * w).reshape(h, w)
+    want = oracle.sobel3(a, ("gx", "gy", "mag"))
+    s = mats(R, a, where)
+    mag, gx, gy = (out_like(R, s, where) for _ in range(3))
+    R.imgproc.sobel_mag(s, mag, gx, gy)
+    assert_f32(gx.to_numpy(), want["gx"], f"sobel gx {shape} {where}", max_ulp=0)
+    assert_f32(gy.to_numpy(), want["gy"], f"sobel gy {shape} {where}", max_ulp=0)
+    assert_f32(mag.to_numpy(), want["mag"], f"sobel mag {shape} {where}", max_ulp=1)
+    # magnitude only (the fused config-3 form)
+    m2 = out_like(R, s, where)
+    R.imgproc.sobel_mag(s, m2)
+    assert_f32(m2.to_numpy(), want["mag"], f"sobel mag-only {shape} {where}", max_ulp=1)
+
+
+def test_sobel_cfg3_full_size(rcv, oracle, golden):
+    """BASELINE.json config 3: 1920x1080 f32; plus the OpenCV tolerance pin."""
+    R = rcv
+    a = oracle.fill_f32(3, 1080 * 1920).reshape(1080, 1920)
+    oracle.set_threads(8)
+    want = oracle.sobel3(a, ("mag",))["mag"]
+    oracle.set_threads(1)
+    s = mats(R, a, "device")
+    m = s.like()
+    R.imgproc.sobel_mag(s, m)
+    assert_f32(m.to_numpy(), want, "sobel cfg3", max_ulp=1)
+    H, W = [int(x) for x in golden["shape"]]
+    f = oracle.fill_f32(9, H * W).reshape(H, W)
+    d = R.Mat.empty()
+    R.imgproc.sobel_mag(R.Mat.from_numpy(f), d)
+    assert np.abs(d.to_numpy() - golden["sobel_mag"]).max() < 4e-6
+
+
+# ---- resize -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("case", [((61, 83, 3), (37, 64)), ((61, 83, 3), (122, 166)), ((61, 83, 3), (30, 41)),
+                                  ((64, 96, 3), (16, 24)), ((128, 256, 3), (32, 64)), ((61, 83, 1), (15, 20)),
+                                  ((40, 40, 4), (100, 7)), ((5, 5, 3), (1, 1)), ((1, 1, 3), (4, 6)), ((64, 64, 3), (32, 32))])
+def test_resize_u8(rcv, oracle, where, case):
+    R = rcv
+    (h, w, cn), (dr, dc) = case
+    a = oracle.fill_u8(60 + h, h * w * cn).reshape(h, w, cn)
+    if cn == 1:
+        a = a.reshape(h, w)
+    s = mats(R, a, where)
+    d = out_like(R, s, where, rows=dr, cols=dc)
+    R.imgproc.resize(s, d, (dc, dr) if where == "host" else None)
+    assert_same(d.to_numpy(), oracle.resize_bilinear(a, dr, dc), f"resize {case} {where}")
+
+
+def test_resize_4x_fast_path_equals_general_model(rcv, oracle, golden):
+    R = rcv
+    big = oracle.fill_u8(11, 64 * 96 * 3).reshape(64, 96, 3)
+    s = mats(R, big, "device")
+    d = s.like(rows=16, cols=24)
+    R.imgproc.resize(s, d)
+    assert_same(d.to_numpy(), golden["resize4x_bgr"], "4x vs OpenCV golden")
+    R.imgproc.set_option("resize.force_generic", 1)
+    try:
+        d2 = s.like(rows=16, cols=24)
+        R.imgproc.resize(s, d2)
+        assert_same(d2.to_numpy(), d.to_numpy(), "4x fast path vs general kernel")
+    finally:
+        R.imgproc.set_option("resize.force_generic", 0)
+
+
+def test_resize_f32(rcv, oracle):
+    R = rcv
+    a = oracle.fill_f32(61, 61 * 83).reshape(61, 83)
+    for dr, dc in ((30, 41), (100, 200), (61, 83)):
+        d = R.Mat.empty()
+        R.imgproc.resize(R.Mat.from_numpy(a), d, (dc, dr))
+        assert_f32(d.to_numpy(), oracle.resize_bilinear(a, dr, dc), f"resize f32 {dr}x{dc}", max_ulp=0)
+
+
+# ---- warpAffine -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("shape,angle,scale", [((61, 83), 15.0, 1.0), ((128, 128), 15.0, 1.0), ((50, 200), -37.0, 1.3),
+                                               ((200, 50), 90.0, 1.0), ((64, 64), 0.0, 1.0), ((33, 47), 180.0, 0.5)])
+def test_warp_affine_f32(rcv, oracle, where, shape, angle, scale):
+    R = rcv
+    h, w = shape
+    a = oracle.fill_f32(70 + h, h * w).reshape(h, w)
+    M = R.imgproc.get_rotation_matrix_2d(((w - 1) / 2, (h - 1) / 2), angle, scale)
+    assert (M.ravel() == oracle.rotation_matrix((w - 1) / 2, (h - 1) / 2, angle, scale)).all()
+    s = mats(R, a, where)
+    d = out_like(R, s, where)
+    R.imgproc.warp_affine(s, d, M, border_value=0.25)
+    assert_f32(d.to_numpy(), oracle.warp_affine(a, M.ravel(), border_value=0.25), f"warp {shape} {angle} {where}", max_ulp=1)
+
+
+def test_warp_affine_u8_and_inverse_map(rcv, oracle):
+    R = rcv
+    a = oracle.fill_u8(71, 61 * 83 * 3).reshape(61, 83, 3)
+    M = R.imgproc.get_rotation_matrix_2d((41.0, 30.0), 15.0, 1.1)
+    d = R.Mat.empty()
+    R.imgproc.warp_affine(R.Mat.from_numpy(a), d, M, dsize=(100, 70), border_value=7)
+    assert_same(d.to_numpy(), oracle.warp_affine(a, M.ravel(), dsize=(70, 100), border_value=7), "warp u8")
+    iM = oracle.invert_affine(M.ravel())
+    R.imgproc.warp_affine(R.Mat.from_numpy(a), d, iM.reshape(2, 3), dsize=(100, 70), inverse_map=True, border_value=7)
+    assert_same(d.to_numpy(), oracle.warp_affine(a, iM, dsize=(70, 100), inverse_map=True, border_value=7), "warp u8 inverse")
+
+
+# ---- batches ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("where", ["device", "pinned", "host"])
+def test_gaussian_batch(rcv, oracle, where):
+    R = rcv
+    n, h, w = 6, 131, 517
+    frames = [oracle.fill_u8(80 + j, h * w * 3).reshape(h, w, 3) for j in range(n)]
+    if where == "device":
+        sb = R.Mat.device_batch(n, h, w, 3)
+        db = R.Mat.device_batch(n, h, w, 3)
+        from rustcv_b200 import _ffi as F
+        for j in range(n):
+            F.check(F.lib.rcv_mat_upload(C.byref(R.Mat.from_numpy(frames[j]).c()), C.byref(sb[j].c())))
+        before = R.imgproc.launch_count()
+        R.imgproc.gaussian_blur_batch(sb, db)
+        assert R.imgproc.launch_count() - before == 1, "a uniform device batch is ONE launch"
+        outs = [db[j].to_numpy() for j in range(n)]
+        sb.free()
+        db.free()
+    else:
+        srcs = [mats(R, f, where) for f in frames]
+        dsts = [s.like() for s in srcs]
+        R.imgproc.gaussian_blur_batch(srcs, dsts)
+        outs = [d.to_numpy() for d in dsts]
+    for j in range(n):
+        assert_same(outs[j], oracle.gaussian_blur(frames[j], (5, 5)), f"batch {where} frame {j}")
+
+
+def test_other_batches(rcv, oracle):
+    R = rcv
+    n = 5
+    # Sobel
+    fr = [oracle.fill_f32(90 + j, 70 * 250).reshape(70, 250) for j in range(n)]
+    sb = R.Mat.device_batch(n, 70, 250, 1, R.F32)
+    db = R.Mat.device_batch(n, 70, 250, 1, R.F32)
+    from rustcv_b200 import _ffi as F
+    for j in range(n):
+        F.check(F.lib.rcv_mat_upload(C.byref(R.Mat.from_numpy(fr[j]).c()), C.byref(sb[j].c())))
+    R.imgproc.sobel_mag_batch(sb, db)
+    for j in range(n):
+        assert_f32(db[j].to_numpy(), oracle.sobel3(fr[j])["mag"], f"sobel batch {j}", max_ulp=1)
+    # warpAffine on the same frames
+    M = R.imgproc.get_rotation_matrix_2d((124.5, 34.5), 15.0)
+    R.imgproc.warp_affine_batch(sb, db, M)
+    for j in range(n):
+        assert_f32(db[j].to_numpy(), oracle.warp_affine(fr[j], M.ravel()), f"warp batch {j}", max_ulp=1)
+    sb.free()
+    db.free()
+    # resize 4x, host batch through the staging ring (n > ring depth)
+    fr = [oracle.fill_u8(95 + j, 64 * 128 * 3).reshape(64, 128, 3) for j in range(n)]
+    srcs = [R.Mat.from_numpy(f) for f in fr]
+    dsts = [R.Mat.new(16, 32, 3) for _ in fr]
+    R.imgproc.resize_batch(srcs, dsts)
+    for j in range(n):
+        assert_same(dsts[j].to_numpy(), oracle.resize_bilinear(fr[j], 16, 32), f"resize batch {j}")
+    # cvtColor batch
+    yu = [oracle.fill_u8(99 + j, 48 * 64 * 2).reshape(48, 64, 2) for j in range(n)]
+    srcs = [R.Mat.from_numpy(f) for f in yu]
+    dsts = [R.Mat.new(48, 64, 3) for _ in yu]
+    R.imgproc.cvt_color_batch(srcs, dsts, R.imgproc.COLOR_YUYV2BGR)
+    for j in range(n):
+        assert_same(dsts[j].to_numpy(), oracle.yuyv_to_bgr(yu[j]), f"cvt batch {j}")
+
+
+def test_fused_yuyv_gaussian(rcv, oracle):
+    R = rcv
+    src = oracle.fill_u8(1, 480 * 640 * 2).reshape(480, 640, 2)
+    d = R.Mat.empty()
+    R.imgproc.yuyv_to_bgr_gaussian5(R.Mat.from_numpy(src), d)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(oracle.yuyv_to_bgr(src), (5, 5)), "yuyv->bgr->gauss5")
+
+
+# ---- full BASELINE.json sizes: goldens and size-independent properties ---------------------------------------------
+def test_cfg2_full_size_golden_crc(rcv, oracle):
+    """3840x2160 BGR, SplitMix64 seed 2: dst CRC32 827081c8 (== OpenCV)."""
+    R = rcv
+    img = oracle.fill_u8(2, 2160 * 3840 * 3).reshape(2160, 3840, 3)
+    for where in ("device", "host"):
+        s = mats(R, img, where)
+        d = out_like(R, s, where)
+        R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+        got = d.to_numpy()
+        assert oracle.crc32(got) == 0x827081C8, where
+        assert got[0, 0].tolist() == [123, 104, 111] and got[1079, 1919].tolist() == [97, 153, 135]
+
+
+def test_cfg2_properties_at_full_size(rcv, oracle):
+    R = rcv
+    h, w = 2160, 3840
+    # constant image is a fixed point (taps sum to 256, single rounding)
+    c = np.full((h, w, 3), 201, np.uint8)
+    s = mats(R, c, "device")
+    d = s.like()
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    assert (d.to_numpy() == 201).all()
+    # channel independence + 180-degree symmetry: blur(flip(x)) == flip(blur(x))
+    img = oracle.fill_u8(5, h * w * 3).reshape(h, w, 3)
+    s = mats(R, img, "device")
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    a = d.to_numpy()
+    s2 = mats(R, np.ascontiguousarray(img[::-1, ::-1]), "device")
+    R.imgproc.gaussian_blur(s2, d, (5, 5), 0.0)
+    assert (d.to_numpy()[::-1, ::-1] == a).all()
+    s3 = mats(R, np.ascontiguousarray(img[:, :, ::-1]), "device")
+    R.imgproc.gaussian_blur(s3, d, (5, 5), 0.0)
+    assert (d.to_numpy()[:, :, ::-1] == a).all()
+    # the fast kernel and the general kernel agree on the whole frame
+    R.imgproc.set_option("gauss.force_generic", 1)
+    try:
+        R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    finally:
+        R.imgproc.set_option("gauss.force_generic", 0)
+    assert (d.to_numpy() == a).all()
+
+
+def test_cfg4_full_size_golden_crc(rcv, oracle):
+    """7680x4320 -> 1920x1080 BGR, seed 4: dst CRC32 31a84a85 (== OpenCV INTER_LINEAR)."""
+    R = rcv
+    s = mats(R, oracle.fill_u8(4, 4320 * 7680 * 3).reshape(4320, 7680, 3), "device")
+    d = s.like(rows=1080, cols=1920)
+    R.imgproc.resize(s, d)
+    assert oracle.crc32(d.to_numpy()) == 0x31A84A85
+
+
+def test_cfg5_warp_full_size_properties(rcv, oracle):
+    """4096x4096 f32, 15 degrees about the centre: rows sampled against the oracle."""
+    R = rcv
+    n = 4096
+    a = oracle.fill_f32(5, n * n).reshape(n, n)
+    assert oracle.crc32(a) == 0xC8A39EB9
+    M = R.imgproc.get_rotation_matrix_2d(((n - 1) / 2, (n - 1) / 2), 15.0)
+    s = mats(R, a, "device")
+    d = s.like()
+    R.imgproc.warp_affine(s, d, M)
+    got = d.to_numpy()
+    oracle.set_threads(8)
+    want = oracle.warp_affine(a, M.ravel())
+    oracle.set_threads(1)
+    assert_f32(got, want, "warp cfg5", max_ulp=1)
+    # identity warp is exact
+    I = np.array([[1.0, 0, 0], [0, 1.0, 0]])
+    R.imgproc.warp_affine(s, d, I)
+    assert (d.to_numpy() == a).all()
