@@ -110,16 +110,20 @@ int copy_in(const RcvMat *m, const Staged &st, cudaStream_t s) {
   return RCV_OK;
 }
 
-int copy_out(const RcvMat *m, const Staged &st, cudaStream_t s) {
+// written_cols < cols: the op leaves the trailing columns of dst untouched (the odd last
+// pixel of a YUYV row, videoio/mod.rs:350), so they must not be overwritten by scratch.
+int copy_out(const RcvMat *m, const Staged &st, cudaStream_t s, int written_cols = -1) {
   if (!st.staged || m->rows == 0 || m->cols == 0) return RCV_OK;
-  RCV_CUDA(cudaMemcpy2DAsync(m->data, m->step, st.v.data, st.v.step, mat_row_bytes(m), m->rows,
-                             cudaMemcpyDeviceToHost, s));
+  size_t rb = mat_row_bytes(m);
+  if (written_cols >= 0 && written_cols < m->cols) rb = (size_t)written_cols * m->channels * elem_size(m->depth);
+  if (rb == 0) return RCV_OK;
+  RCV_CUDA(cudaMemcpy2DAsync(m->data, m->step, st.v.data, st.v.step, rb, m->rows, cudaMemcpyDeviceToHost, s));
   return RCV_OK;
 }
 
 // Runs `launch(ctx, src_batch, dst_batch, stream)` for one src -> one dst.
 template <class F>
-int run_unary(const RcvMat *src, RcvMat *dst, F launch) {
+int run_unary(const RcvMat *src, RcvMat *dst, F launch, int written_cols = -1) {
   const RcvMat *mats[2] = {src, dst};
   Ctx *c = pick_ctx(mats, 2);
   if (!c) return RCV_ERR_NOT_INIT;
@@ -129,7 +133,7 @@ int run_unary(const RcvMat *src, RcvMat *dst, F launch) {
   RCV_TRY(stage_alloc(c, dst, SCR_STAGE_OUT0, &so));
   RCV_TRY(copy_in(src, si, c->stream));
   RCV_TRY(launch(c, single(si.v), single(so.v), c->stream));
-  RCV_TRY(copy_out(dst, so, c->stream));
+  RCV_TRY(copy_out(dst, so, c->stream, written_cols));
   if (ctx_blocking() || si.staged || so.staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
   return RCV_OK;
 }
@@ -160,7 +164,7 @@ int check_batch_geometry(const RcvMat *m, int n, const char *name) {
 }
 
 template <class F>
-int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch) {
+int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch, int written_cols = -1) {
   if (n == 0) return RCV_OK;
   std::vector<const RcvMat *> mats;
   for (int i = 0; i < n; ++i) {
@@ -203,7 +207,7 @@ int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch) {
     RCV_TRY(launch(c, single(in.v), single(out.v), c->stream));
     RCV_CUDA(cudaEventRecord(c->ev_k[k], c->stream));
     RCV_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
-    RCV_TRY(copy_out(&dsts[i], out, c->s_out));
+    RCV_TRY(copy_out(&dsts[i], out, c->s_out, written_cols));
     RCV_CUDA(cudaEventRecord(c->ev_out[k], c->s_out));
   }
   RCV_CUDA(cudaStreamSynchronize(c->s_out));
@@ -233,6 +237,12 @@ int check_cvt(const RcvMat *src, const RcvMat *dst, int code) {
   if (code == RCV_COLOR_BGR2XRGB32 && dst->rows > 0 && ((dst->step & 3) || ((uintptr_t)dst->data & 3)))
     return fail(RCV_ERR_SIZE, "XRGB32 dst must be 4-byte aligned");
   return check_same_size(src, dst, "cvtColor");
+}
+
+// 4:2:2 formats convert cols/2 macro-pixels per row: an odd last column is not written
+int cvt_written_cols(const RcvMat *src, int code) {
+  if (code == RCV_COLOR_YUYV2BGR || code == RCV_COLOR_UYVY2BGR || code == RCV_COLOR_YUYV2GRAY) return src->cols & ~1;
+  return -1;
 }
 
 int check_filter_pair(const RcvMat *src, const RcvMat *dst, const char *what) {
@@ -323,7 +333,7 @@ int rcv_cvt_color(const RcvMat *src, RcvMat *dst, int32_t code) {
   RCV_TRY(check_cvt(src, dst, code));
   return run_unary(src, dst, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_cvt(c, s, d, code, st);
-  });
+  }, cvt_written_cols(src, code));
 }
 
 int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code) {
@@ -334,7 +344,7 @@ int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t cod
   RCV_TRY(check_cvt(&srcs[0], &dsts[0], code));
   return run_batch(srcs, dsts, n, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_cvt(c, s, d, code, st);
-  });
+  }, cvt_written_cols(&srcs[0], code));
 }
 
 int rcv_yuyv_to_bgr(const RcvMat *src, RcvMat *dst) { return rcv_cvt_color(src, dst, RCV_COLOR_YUYV2BGR); }

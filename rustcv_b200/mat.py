@@ -177,6 +177,7 @@ class Mat:
             c.data = self.data.ctypes.data if self.data is not None and self.data.size else None
         c.rows, c.cols, c.step = self.rows, self.cols, self.step
         c.channels, c.depth, c.loc, c.device = self.channels, self.depth, self.loc, self.device
+        c._keep = self  # the POD borrows self.data: keep the owner alive as long as the POD
         self._c = c
         return c
 

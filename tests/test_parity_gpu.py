@@ -63,6 +63,12 @@ def mats(R, a, where, step=None):
     return R.Mat.from_numpy(a).upload()
 
 
+def upload_into(R, a, dev_mat):
+    from rustcv_b200 import _ffi as F
+    h = R.Mat.from_numpy(a)  # keep the host Mat alive across the call
+    F.check(F.lib.rcv_mat_upload(C.byref(h.c()), C.byref(dev_mat.c())))
+
+
 def out_like(R, src, where, channels=None, depth=None, rows=None, cols=None):
     if where == "host":
         return R.Mat.empty()
@@ -462,7 +468,7 @@ def test_gaussian_batch(rcv, oracle, where):
         db = R.Mat.device_batch(n, h, w, 3)
         from rustcv_b200 import _ffi as F
         for j in range(n):
-            F.check(F.lib.rcv_mat_upload(C.byref(R.Mat.from_numpy(frames[j]).c()), C.byref(sb[j].c())))
+            upload_into(R, frames[j], sb[j])
         before = R.imgproc.launch_count()
         R.imgproc.gaussian_blur_batch(sb, db)
         assert R.imgproc.launch_count() - before == 1, "a uniform device batch is ONE launch"
@@ -487,7 +493,7 @@ def test_other_batches(rcv, oracle):
     db = R.Mat.device_batch(n, 70, 250, 1, R.F32)
     from rustcv_b200 import _ffi as F
     for j in range(n):
-        F.check(F.lib.rcv_mat_upload(C.byref(R.Mat.from_numpy(fr[j]).c()), C.byref(sb[j].c())))
+        upload_into(R, fr[j], sb[j])
     R.imgproc.sobel_mag_batch(sb, db)
     for j in range(n):
         assert_f32(db[j].to_numpy(), oracle.sobel3(fr[j])["mag"], f"sobel batch {j}", max_ulp=1)
