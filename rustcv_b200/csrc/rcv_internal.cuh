@@ -66,6 +66,7 @@ enum ScratchSlot {
   SCR_TABLE_X = 24,
   SCR_TABLE_Y = 25,
   SCR_TAPS = 26,
+  SCR_COUNTER = 28,   // work-stealing counter of the strip kernels
   SCR_FUSE_TMP = 27,  // intermediate BGR of the two-pass YUYV->BGR->Gaussian chain
   SCR_COUNT = 32
 };

@@ -104,6 +104,7 @@ struct StripParams {
   int n_frames;
   int vec_store;  // all outputs 16-byte aligned (base, step, frame stride)
   long long total_items;
+  unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -140,7 +141,8 @@ struct Gauss5Op {
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
-      V[h] = (r0 + in[h]) + ((r1 + r3) << 2) + r2 * 6u;  // <= 4080 per lane
+      // + 8 per lane: the horizontal taps sum to 16, so this is the final "+128" rounding term
+      V[h] = (r0 + in[h] + 0x00080008u) + ((r1 + r3) << 2) + r2 * 6u;  // <= 4088 per lane
       win[J][h] = in[h];
     }
     if (!emit) return;
@@ -180,14 +182,14 @@ struct Gauss5Op {
           const int wd = p >> 2, ph = p & 3;
           t[j] = ph == 0 ? lo[wd] : ph == 1 ? hi[wd] : ph == 2 ? loS[wd] : hiS[wd];
         }
-        H[e] = (t[0] + t[4] + 0x00800080u) + ((t[1] + t[3]) << 2) + t[2] * 6u;  // <= 65408 per lane
+        H[e] = (t[0] + t[4]) + ((t[1] + t[3]) << 2) + t[2] * 6u;  // <= 16 * 4088 = 65408 per lane
       }
       ow[k] = __byte_perm(H[0], H[1], 0x7351);  // high bytes of the four 16-bit lanes, in byte order
     }
     uint8_t *o = outp[0];
     if (nvalid == 16 && vec) {
       *(uint4 *)o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    } else {
+    } else if (nvalid > 0) {  // ragged right edge / unaligned dst only; halo lanes store nothing
 #pragma unroll
       for (int b = 0; b < 16; ++b)
         if (b < nvalid) o[b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
@@ -254,7 +256,7 @@ struct Sobel3Op {
     if (!o) return;
     if (nvalid == 16 && vec) {
       *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
+    } else if (nvalid > 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c * 4 < nvalid) o[c] = v[c];
@@ -289,7 +291,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   const long long total_warps = (long long)gridDim.x * NW;
   Op op;
 
-  for (long long item = (long long)blockIdx.x * NW + warp; item < p.total_items; item += total_warps) {
+  long long item = (long long)blockIdx.x * NW + warp;
+  while (item < p.total_items) {
+    // claim the next item now; the atomic's latency hides behind this item's work
+    unsigned long long claimed = 0;
+    if (p.next_item != nullptr && lane == 0) claimed = atomicAdd(p.next_item, 1ULL);
     const int strip = (int)(item % p.strips);
     const long long t = item / p.strips;
     const int band = (int)(t % p.bands);
@@ -409,6 +415,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       }
     }
     __syncwarp();  // all lanes done with the ring before the next item's prologue refills it
+    if (p.next_item != nullptr)
+      item = total_warps + (long long)__shfl_sync(0xffffffffu, claimed, 0);
+    else
+      item += total_warps;
   }
 }
 
@@ -425,21 +435,35 @@ bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
   return aligned16(src) && src.v.rows >= min_rows && src.v.cols >= min_cols;
 }
 
-// picks the band height: bands of 8k+4 rows (so band+4 feeds fill whole 8-row chunks),
-// enough items for ~2 rounds over the resident warps, at most 244 rows.
+// Picks the band height.  Every band costs 2*hv warm-up rows, and the kernel's time is
+// set by the warp that feeds the most rows, so: try k = 1..16 rounds over the resident
+// warps, size the bands so the items fill k rounds, make (band + 2*hv) a whole number of
+// R-row chunks, and keep the candidate with the fewest rows fed by the busiest warp.
 static int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv) {
   int64_t forced = opt_get(optname, 0);
   if (forced > 0) return (int)forced;
-  long long warps = (long long)ctx_sm_count(c) * kNW;
-  long long strips_total = (long long)strips * n;
-  // rows per item so that items ~= 3 * warps
-  long long want = ((long long)rows * strips_total) / (3 * warps);
-  int br = (int)want;
-  if (br > 244) br = 244;
-  if (br < 28) br = 28;
-  br = ((br + 2 * hv) / kR) * kR - 2 * hv;  // (br + 2hv) multiple of R
-  if (br < kR) br = kR;
-  return br;
+  const long long warps = (long long)ctx_sm_count(c) * kNW;
+  const long long strips_total = (long long)strips * n;
+  const int min_band = 4 * kR - 2 * hv;
+  long long best_cost = -1;
+  int best = rows;
+  for (int k = 1; k <= 16; ++k) {
+    long long B = (k * warps) / strips_total;
+    if (B < 1) B = 1;
+    int br = (int)((rows + B - 1) / B);
+    if (br < min_band) br = min_band;
+    br = ((br + 2 * hv + kR - 1) / kR) * kR - 2 * hv;
+    if (br > rows) br = rows;
+    const long long bands = (rows + br - 1) / br;
+    const long long items = bands * strips_total;
+    const long long rounds = (items + warps - 1) / warps;
+    const long long cost = rounds * (br + 2 * hv);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = br;
+    }
+  }
+  return best;
 }
 
 template <class Op>
@@ -465,6 +489,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   p.bands = ceil_div(p.rows, p.band_rows);
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
+  p.next_item = nullptr;
 
   auto kern = k_strip<Op, kR, kS, kNW>;
   const int smem = kNW * kS * kR * kTileBytes + kNW * kS * 8;
@@ -473,6 +498,12 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   int64_t grid_opt = opt_get("strip.grid", 0);
   int grid = (int)(blocks < ctx_sm_count(c) ? blocks : ctx_sm_count(c));
   if (grid_opt > 0) grid = (int)grid_opt;
+  if (opt_get("strip.dynamic", 1) != 0 && p.total_items > (long long)grid * kNW) {
+    void *ctr = nullptr;
+    RCV_TRY(ctx_scratch(c, SCR_COUNTER, sizeof(unsigned long long), &ctr));
+    RCV_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+    p.next_item = (unsigned long long *)ctr;
+  }
   kern<<<grid, kNW * 32, smem, s>>>(tmap, p);
   count_launch();
   RCV_CUDA(cudaGetLastError());
