@@ -112,6 +112,25 @@ struct StripParams {
 //   out = (sum_ij k_i k_j p + 128) >> 8, k = {1,4,6,4,1}   (oracle: orc_sepfilter_u8_q8
 //   with Q8 taps {16,64,96,64,16}: (sum ky kx p + 32768) >> 16 is the same number)
 // ---------------------------------------------------------------------------------------
+// Integer ops pinned with inline PTX so that NVVM cannot re-associate the sums (it turns
+// the 4-op forms below into 5): ptxas still picks the pipe (IADD3 / IMAD.IADD / LEA).
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <int M>
+__device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(M), "r"(c));
+  return d;
+}
+
 template <int CN>
 struct Gauss5Op {
   static constexpr int HV = 2;   // rows of vertical halo
@@ -128,7 +147,8 @@ struct Gauss5Op {
   }
 
   // J = (feed index) & 3, compile time: win[J] holds the oldest row.
-  template <int J>
+  // FAST: interior rows of an aligned, non-ragged strip -- always emits, lanes store 16 B or nothing.
+  template <int J, bool FAST>
   __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
     uint32_t in[8];
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -137,38 +157,55 @@ struct Gauss5Op {
       in[2 * k] = __byte_perm(w[k], 0, 0x4240);      // (b0, b2) as 16-bit lanes
       in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);  // (b1, b3)
     }
+    // vertical: V = r0 + 4 r1 + 6 r2 + 4 r3 + r4 (+8 per lane: with horizontal taps summing
+    // to 16 that is the final "+128" rounding term).  V <= 4088 per 16-bit lane.
     uint32_t V[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
-      uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
-      // + 8 per lane: the horizontal taps sum to 16, so this is the final "+128" rounding term
-      V[h] = (r0 + in[h] + 0x00080008u) + ((r1 + r3) << 2) + r2 * 6u;  // <= 4088 per lane
+      const uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
+      const uint32_t a = add3(r0, in[h], 0x00080008u);
+      const uint32_t b = add2(r1, r3);
+      V[h] = madc<6>(r2, madc<4>(b, a));
       win[J][h] = in[h];
     }
-    if (!emit) return;
+    if (!FAST && !emit) return;
 
-    // words -2..5 of the vertical sums (index +2): own 0..3, neighbours by shuffle
-    uint32_t lo[8], hi[8];
+    // Vertical sums of words -2..5 (index +2) as lo = (byte0, byte2) / hi = (byte1, byte3) pairs and
+    // the odd-phase pairs S[i] = (byte 2|3 of word i, byte 0|1 of word i+1).  Own words 0..3; the
+    // neighbours' by shuffle: from the left lane its word 3 and its S of words 2-3, from the right
+    // lane its word 0 and its S of words 0-1.
+    uint32_t lo[8], hi[8], loS[7], hiS[7];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       lo[k + 2] = V[2 * k];
       hi[k + 2] = V[2 * k + 1];
     }
-    lo[0] = __shfl_up_sync(0xffffffffu, V[4], 1);
-    hi[0] = __shfl_up_sync(0xffffffffu, V[5], 1);
-    lo[1] = __shfl_up_sync(0xffffffffu, V[6], 1);
-    hi[1] = __shfl_up_sync(0xffffffffu, V[7], 1);
-    lo[6] = __shfl_down_sync(0xffffffffu, V[0], 1);
-    hi[6] = __shfl_down_sync(0xffffffffu, V[1], 1);
-    lo[7] = __shfl_down_sync(0xffffffffu, V[2], 1);
-    hi[7] = __shfl_down_sync(0xffffffffu, V[3], 1);
-    // odd-phase pairs: loS[i] = (byte 2 of word i, byte 0 of word i+1), hiS[i] = (byte 3, byte 1 of next)
-    uint32_t loS[7], hiS[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 2; i < 5; ++i) {
       loS[i] = __byte_perm(lo[i], lo[i + 1], 0x5432);
       hiS[i] = __byte_perm(hi[i], hi[i + 1], 0x5432);
     }
+    lo[1] = __shfl_up_sync(0xffffffffu, lo[5], 1);
+    hi[1] = __shfl_up_sync(0xffffffffu, hi[5], 1);
+    loS[0] = __shfl_up_sync(0xffffffffu, loS[4], 1);
+    hiS[0] = __shfl_up_sync(0xffffffffu, hiS[4], 1);
+    lo[6] = __shfl_down_sync(0xffffffffu, lo[2], 1);
+    hi[6] = __shfl_down_sync(0xffffffffu, hi[2], 1);
+    loS[6] = __shfl_down_sync(0xffffffffu, loS[2], 1);
+    hiS[6] = __shfl_down_sync(0xffffffffu, hiS[2], 1);
+    loS[1] = __byte_perm(lo[1], lo[2], 0x5432);
+    hiS[1] = __byte_perm(hi[1], hi[2], 0x5432);
+    loS[5] = __byte_perm(lo[5], lo[6], 0x5432);
+    hiS[5] = __byte_perm(hi[5], hi[6], 0x5432);
+    if constexpr (CN == 4) {  // taps at -8 / +8 bytes land on whole words -2 and 5
+      lo[0] = __shfl_up_sync(0xffffffffu, lo[4], 1);
+      hi[0] = __shfl_up_sync(0xffffffffu, hi[4], 1);
+      lo[7] = __shfl_down_sync(0xffffffffu, lo[3], 1);
+      hi[7] = __shfl_down_sync(0xffffffffu, hi[3], 1);
+    } else {
+      lo[0] = hi[0] = lo[7] = hi[7] = 0;  // never selected: CN <= 3 reaches words -2 / 5 only through S[0] / S[6]
+    }
+
     uint32_t ow[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -182,12 +219,14 @@ struct Gauss5Op {
           const int wd = p >> 2, ph = p & 3;
           t[j] = ph == 0 ? lo[wd] : ph == 1 ? hi[wd] : ph == 2 ? loS[wd] : hiS[wd];
         }
-        H[e] = (t[0] + t[4]) + ((t[1] + t[3]) << 2) + t[2] * 6u;  // <= 16 * 4088 = 65408 per lane
+        H[e] = madc<6>(t[2], madc<4>(add2(t[1], t[3]), add2(t[0], t[4])));  // <= 16 * 4088 = 65408 per lane
       }
       ow[k] = __byte_perm(H[0], H[1], 0x7351);  // high bytes of the four 16-bit lanes, in byte order
     }
     uint8_t *o = outp[0];
-    if (nvalid == 16 && vec) {
+    if (FAST) {
+      if (nvalid == 16) *(uint4 *)o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    } else if (nvalid == 16 && vec) {
       *(uint4 *)o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     } else if (nvalid > 0) {  // ragged right edge / unaligned dst only; halo lanes store nothing
 #pragma unroll
@@ -195,6 +234,7 @@ struct Gauss5Op {
         if (b < nvalid) o[b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
     }
   }
+  static_assert(CN >= 1 && CN <= 4, "the farthest taps (2*CN bytes) must stay within two words");
 };
 
 // ---------------------------------------------------------------------------------------
@@ -216,7 +256,7 @@ struct Sobel3Op {
       for (int h = 0; h < 4; ++h) win[j][h] = 0.0f;
   }
 
-  template <int J>
+  template <int J, bool FAST>
   __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
     constexpr int JJ = J & 1;
     const float pp[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
@@ -230,7 +270,7 @@ struct Sobel3Op {
       d[c + 1] = __fsub_rn(pp[c], pm);
       win[JJ][c] = pp[c];
     }
-    if (!emit) return;
+    if (!FAST && !emit) return;
     s[0] = __shfl_up_sync(0xffffffffu, s[4], 1);
     d[0] = __shfl_up_sync(0xffffffffu, d[4], 1);
     s[5] = __shfl_down_sync(0xffffffffu, s[1], 1);
@@ -311,7 +351,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     const bool right_edge = (p.row_bytes < x0 + kOutBytes + kLaneBytes);
     const int xr = kLaneBytes + (p.row_bytes - x0);  // tile byte offset of the first byte past the row
     const bool top = (ys < 0);
-    const bool bottom = (y1 == p.rows);
+    const bool bottom = (y1 + HV > p.rows);  // the fed rows run past the last image row
+    const bool fast_strip = p.vec_store != 0 && !right_edge;  // full 16-byte stores in lanes 1..30
 
     // this lane's slice of the outputs
     const int xl = x0 + (lane - 1) * kLaneBytes;
@@ -389,6 +430,22 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       if (lane == 0 && c >= 1 && c - 1 + S < n_chunks) issue(c - 1 + S);
 
       // ---- rows of this chunk ----
+      if (fast_strip && c * R >= 2 * HV && c * R + R <= n_feed) {
+        // interior chunk of an aligned, non-ragged strip: every row is fed and emitted, no per-row tests
+        const uint32_t rowaddr = tile + lane * kLaneBytes;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const uint4 q = lds128(rowaddr + j * kTileBytes);
+          if ((j & 3) == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
+          if ((j & 3) == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
+          if ((j & 3) == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
+          if ((j & 3) == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
+#pragma unroll
+          for (int k = 0; k < Op::NOUT; ++k)
+            if (optr[k]) optr[k] += p.out[k].step;
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < R / 4; ++g) {
         const int fi0 = c * R + g * 4;
@@ -401,10 +458,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
           if (fi < n_feed) {
             const uint4 q = lds128(rowaddr + j * kTileBytes);
             const bool emit = fi >= 2 * HV;
-            if (j == 0) op.template feed<0>(q, emit, optr, nvalid, p.vec_store != 0);
-            if (j == 1) op.template feed<1>(q, emit, optr, nvalid, p.vec_store != 0);
-            if (j == 2) op.template feed<2>(q, emit, optr, nvalid, p.vec_store != 0);
-            if (j == 3) op.template feed<3>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 0) op.template feed<0, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 1) op.template feed<1, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 2) op.template feed<2, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 3) op.template feed<3, false>(q, emit, optr, nvalid, p.vec_store != 0);
             if (emit) {
 #pragma unroll
               for (int k = 0; k < Op::NOUT; ++k)
@@ -435,35 +492,20 @@ bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
   return aligned16(src) && src.v.rows >= min_rows && src.v.cols >= min_cols;
 }
 
-// Picks the band height.  Every band costs 2*hv warm-up rows, and the kernel's time is
-// set by the warp that feeds the most rows, so: try k = 1..16 rounds over the resident
-// warps, size the bands so the items fill k rounds, make (band + 2*hv) a whole number of
-// R-row chunks, and keep the candidate with the fewest rows fed by the busiest warp.
+// Picks the band height.  Measured on B200 (profiles/README.md, sweep r1d): short bands win
+// although every band re-feeds 2*hv warm-up rows -- the work-claim scheduler balances better
+// with many small items, and the rows in flight across all resident warps then span a few
+// tens of MB (TLB reach, L2-resident halo rows) instead of hundreds.  36 rows (40 fed rows =
+// 5 chunks of R) measured best for the 5x5 Gaussian: 8.04 us per 4K frame vs 8.64 at 60 rows
+// and 10.9 at 244.  Tiny jobs use shorter bands to occupy more warps.
 static int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv) {
   int64_t forced = opt_get(optname, 0);
   if (forced > 0) return (int)forced;
   const long long warps = (long long)ctx_sm_count(c) * kNW;
-  const long long strips_total = (long long)strips * n;
-  const int min_band = 4 * kR - 2 * hv;
-  long long best_cost = -1;
-  int best = rows;
-  for (int k = 1; k <= 16; ++k) {
-    long long B = (k * warps) / strips_total;
-    if (B < 1) B = 1;
-    int br = (int)((rows + B - 1) / B);
-    if (br < min_band) br = min_band;
-    br = ((br + 2 * hv + kR - 1) / kR) * kR - 2 * hv;
-    if (br > rows) br = rows;
-    const long long bands = (rows + br - 1) / br;
-    const long long items = bands * strips_total;
-    const long long rounds = (items + warps - 1) / warps;
-    const long long cost = rounds * (br + 2 * hv);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = br;
-    }
-  }
-  return best;
+  int br = 5 * kR - 2 * hv;
+  const long long items = (long long)strips * n * ((rows + br - 1) / br);
+  if (items < warps) br = 4 * kR - 2 * hv;
+  return br;
 }
 
 template <class Op>
