@@ -1,0 +1,91 @@
+// Exercises the C++ host mirror (rustcv_b200/hostcpp/rustcv_b200.hpp) against the CPU oracle.
+// Reads like the reference's own tests (rustcv-camera/src/decode.rs:234-273).
+//   host_mirror            full run on cuda:0 (exit 0 = parity)
+//   host_mirror --no-gpu   checks the loud failure mode only
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "rustcv_b200.hpp"
+#include "../../oracle/rcv_oracle.h"
+
+using namespace rustcv;
+
+#define EXPECT(cond)                                                  \
+  do {                                                                \
+    if (!(cond)) {                                                    \
+      std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      return 1;                                                       \
+    }                                                                 \
+  } while (0)
+
+int main(int argc, char **argv) {
+  if (argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0) {
+    core::Mat a = core::Mat::create(8, 8, 3), b;
+    Result r = imgproc::gaussian_blur(a, b, {5, 5}, 0.0);
+    EXPECT(!r.is_ok() && r.code == RCV_ERR_NOT_INIT);
+    EXPECT(r.message.find("no CPU fallback") != std::string::npos);
+    std::puts("host_mirror --no-gpu ok");
+    return 0;
+  }
+  EXPECT(init(0).is_ok());
+
+  // decode.rs:235-252 / :255-265 through decode_frame
+  {
+    const uint8_t white[4] = {235, 128, 235, 128}, black[4] = {16, 128, 16, 128};
+    core::Mat m;
+    EXPECT(videoio::decode_frame(white, 4, 2, 1, videoio::YUYV, m).is_ok());
+    for (uint8_t v : m.data) EXPECT(v > 240);
+    EXPECT(videoio::decode_frame(black, 4, 2, 1, videoio::YUYV, m).is_ok());
+    for (uint8_t v : m.data) EXPECT(v < 10);
+    // the facade silently returns on a short source (videoio/mod.rs:346-348); the ABI reports it
+    EXPECT(videoio::decode_frame(white, 3, 2, 1, videoio::YUYV, m).code == RCV_ERR_SIZE);
+    EXPECT(videoio::decode_frame(white, 4, 2, 1, videoio::MJPEG, m).code == RCV_ERR_UNSUPPORTED);
+  }
+  // config 1: SplitMix64 seed 1, 640x480
+  {
+    std::vector<uint8_t> src(640 * 480 * 2), want(640 * 480 * 3);
+    orc_fill_u8(1, src.data(), src.size());
+    core::Mat m;
+    EXPECT(videoio::decode_frame(src.data(), src.size(), 640, 480, videoio::YUYV, m).is_ok());
+    EXPECT(orc_yuyv_to_bgr_facade(src.data(), src.size(), want.data(), want.size(), 640, 480) == 0);
+    EXPECT(m.rows == 480 && m.cols == 640 && m.channels == 3 && m.step == 1920);
+    EXPECT(std::memcmp(m.data.data(), want.data(), want.size()) == 0);
+    EXPECT(orc_crc32(m.data.data(), m.data.size()) == 0x0BF66518u);
+  }
+  // GaussianBlur 5x5 on host Mats and on device-resident Mats
+  {
+    core::Mat src = core::Mat::create(270, 480, 3), dst, want = core::Mat::create(270, 480, 3);
+    orc_fill_u8(2, src.data.data(), src.data.size());
+    orc_gaussian_blur_u8(src.data.data(), src.step, want.data.data(), want.step, 270, 480, 3, 5, 5, 0.0, 0.0);
+    EXPECT(imgproc::gaussian_blur(src, dst, {5, 5}, 0.0).is_ok());
+    EXPECT(dst.data == want.data);
+    core::DeviceMat ds, dd;
+    EXPECT(core::DeviceMat::create(ds, 270, 480, 3).is_ok() && core::DeviceMat::create(dd, 270, 480, 3).is_ok());
+    EXPECT(ds.upload(src).is_ok());
+    EXPECT(imgproc::gaussian_blur(ds, dd, {5, 5}, 0.0).is_ok());
+    core::Mat back;
+    EXPECT(dd.download(back).is_ok());
+    EXPECT(back.data == want.data);
+    // dst geometry is the callee's job for host Mats, exactly like read() (videoio/mod.rs:192-199)
+    EXPECT(dst.rows == 270 && dst.cols == 480 && dst.step == 1440);
+  }
+  // Sobel + magnitude, resize, BGR->Gray
+  {
+    core::Mat f = core::Mat::create(135, 240, 1, core::F32), mag, want = core::Mat::create(135, 240, 1, core::F32);
+    orc_fill_f32(3, (float *)f.data.data(), 135 * 240);
+    orc_sobel3_f32((const float *)f.data.data(), f.step, nullptr, 0, nullptr, 0, (float *)want.data.data(), want.step, 135, 240);
+    EXPECT(imgproc::sobel_magnitude(f, mag).is_ok());
+    EXPECT(mag.data == want.data);
+    core::Mat img = core::Mat::create(64, 96, 3), small, wsmall = core::Mat::create(16, 24, 3), gray, wgray = core::Mat::create(64, 96, 1);
+    orc_fill_u8(11, img.data.data(), img.data.size());
+    orc_resize_bilinear_u8(img.data.data(), img.step, 64, 96, wsmall.data.data(), wsmall.step, 16, 24, 3);
+    EXPECT(imgproc::resize(img, small, {24, 16}).is_ok());
+    EXPECT(small.data == wsmall.data);
+    orc_bgr_to_gray_strided(img.data.data(), img.step, wgray.data.data(), wgray.step, 64, 96);
+    EXPECT(imgproc::cvt_color(img, gray, imgproc::COLOR_BGR2GRAY).is_ok());
+    EXPECT(gray.data == wgray.data);
+  }
+  std::puts("host_mirror ok");
+  return 0;
+}
