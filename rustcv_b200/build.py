@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "librcv_imgproc.so")
 SOURCES = ["context.cu", "tma.cu", "cvt.cu", "stencil.cu", "filter.cu", "geom.cu", "abi.cu"]
-HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(HERE, "..", "include", "rcv_imgproc.h")]
+HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(HERE, "..", "include", "rcv_imgproc.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the f32 specs fix where fused multiply-adds happen (explicit fmaf only).

@@ -9,6 +9,7 @@
 // All gather kernels: HBM/L2-bound, no shared-memory staging needed for the general case;
 // the exact 4x BGR downscale (BASELINE.json config 4) has a 128-bit-load specialisation.
 #include "rcv_internal.cuh"
+#include "tma_ptx.cuh"
 
 #include <cmath>
 #include <vector>
@@ -272,7 +273,103 @@ __global__ void __launch_bounds__(256) k_warp_affine(const WarpArgs a) {
   }
 }
 
-int launch_warp_affine(Ctx *, const DBatch &src, const DBatch &dst, const double iM[6], double border,
+// ---- f32 single channel, TMA-staged source tiles -------------------------------------------
+// A CTA makes one 64x32 dst tile.  The source pixels it can touch lie in the tile's rotated
+// bounding box; one cp.async.bulk.tensor load brings that box (BW x BH floats, out-of-image
+// parts zero-filled) into shared memory, and the four taps per pixel are gathered from shared
+// memory instead of from L1/L2 (a rotated warp row touches ~9 cache lines per tap in global
+// memory: the direct kernel is L1-wavefront bound, 5x off the HBM roofline).  Arithmetic and
+// the in-image tests are exactly those of k_warp_affine / the oracle.
+constexpr int kWarpTW = 64, kWarpTH = 32, kWarpThreads = 256;
+
+struct WarpTileArgs {
+  WarpArgs a;
+  double d0, d3;  // iM[0], iM[3] in f64 for the tile's bounding box
+  int bw, bh;     // box size in pixels
+  int xalign;     // box x origin is a multiple of this many pixels (power of two)
+};
+
+__global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_constant__ CUtensorMap tmap,
+                                                                const WarpTileArgs t) {
+  // no static shared memory in this kernel: the TMA destination must be 128-byte aligned and the
+  // dynamic segment only starts at offset 0 when nothing static precedes it.  The mbarrier lives
+  // behind the tile.
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const WarpArgs &a = t.a;
+  const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * kWarpTH;
+  // bounding box origin from the four tile corners (f64)
+  const double xs[2] = {(double)tx0, (double)(tx0 + kWarpTW - 1)}, ys[2] = {(double)ty0, (double)(ty0 + kWarpTH - 1)};
+  double minx = 1e300, miny = 1e300;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double sx = t.d0 * xs[i] + a.m1 * ys[j] + a.m2;
+      double sy = t.d3 * xs[i] + a.m4 * ys[j] + a.m5;
+      minx = fmin(minx, sx);
+      miny = fmin(miny, sy);
+    }
+  // clamp far-out-of-image boxes so the int conversion and the TMA coordinates stay sane
+  minx = fmin(fmax(minx, -1.0e6), 1.0e6 + a.scols);
+  miny = fmin(fmax(miny, -1.0e6), 1.0e6 + a.srows);
+  // the box starts on a 16-byte boundary of the row (4 floats): TMA rejects other inner offsets
+  const int bx0 = ((int)floor(minx) - 1) & ~(t.xalign - 1), by0 = (int)floor(miny) - 1;
+  const uint32_t tile = smem_u32(smem_raw), barp = tile + (((uint32_t)(t.bw * t.bh * 4) + 15u) & ~15u);
+  if (threadIdx.x == 0) {
+    mbar_init(barp, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+    mbar_expect_tx(barp, (uint32_t)(t.bw * t.bh * 4));
+    tma_load_3d(tile, &tmap, barp, bx0, by0, (int)blockIdx.z);
+  }
+  __syncthreads();  // barrier init visible to all waiters
+  const int lx = threadIdx.x & 63, ly0 = threadIdx.x >> 6;
+  const int x = tx0 + lx;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  bool waited = false;
+#pragma unroll 2
+  for (int k = 0; k < kWarpTH / 4; ++k) {
+    const int y = ty0 + ly0 + 4 * k;
+    const float bx = __double2float_rn(__dadd_rn(__dmul_rn(a.m1, (double)y), a.m2));
+    const float by = __double2float_rn(__dadd_rn(__dmul_rn(a.m4, (double)y), a.m5));
+    const float sx = fmaf(a.m0, (float)x, bx);
+    const float sy = fmaf(a.m3, (float)x, by);
+    const float flx = floorf(sx), fly = floorf(sy);
+    const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
+    const bool inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
+    const int ix = inside ? (int)flx : 0, iy = inside ? (int)fly : 0;
+    const bool x0ok = inside && ix >= 0, x1ok = inside && ix + 1 < a.scols;
+    const bool y0ok = inside && iy >= 0, y1ok = inside && iy + 1 < a.srows;
+    if (!waited) {
+      mbar_wait(barp, 0);
+      waited = true;
+    }
+    const int cx = ix - bx0, cy = iy - by0;  // tap (0,0) inside the box
+    const bool inbox = (unsigned)cx < (unsigned)(t.bw - 1) && (unsigned)cy < (unsigned)(t.bh - 1);
+    float p00 = a.border, p01 = a.border, p10 = a.border, p11 = a.border;
+    if (inbox) {
+      const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
+      const float v00 = lds_f32(p), v01 = lds_f32(p + 4), v10 = lds_f32(p + t.bw * 4), v11 = lds_f32(p + t.bw * 4 + 4);
+      if (y0ok && x0ok) p00 = v00;
+      if (y0ok && x1ok) p01 = v01;
+      if (y1ok && x0ok) p10 = v10;
+      if (y1ok && x1ok) p11 = v11;
+    } else if (inside) {  // cannot happen for sane boxes; keeps the result exact regardless
+      const float *r0 = (const float *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
+      const float *r1 = (const float *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
+      if (y0ok && x0ok) p00 = __ldg(r0 + ix);
+      if (y0ok && x1ok) p01 = __ldg(r0 + ix + 1);
+      if (y1ok && x0ok) p10 = __ldg(r1 + ix);
+      if (y1ok && x1ok) p11 = __ldg(r1 + ix + 1);
+    }
+    const float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
+    const float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
+    const float v = fmaf(fy, __fsub_rn(q1, q0), q0);
+    if (x < a.dcols && y < a.drows) ((float *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)y * a.dstep))[x] = v;
+  }
+}
+
+int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const double iM[6], double border,
                        cudaStream_t s) {
   if (dst.v.rows == 0 || dst.v.cols == 0 || src.n == 0) return RCV_OK;
   if (src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "batch too large");
@@ -295,6 +392,36 @@ int launch_warp_affine(Ctx *, const DBatch &src, const DBatch &dst, const double
   a.m4 = iM[4];
   a.m5 = iM[5];
   a.border = src.v.depth == RCV_U8 ? (float)(int)border : (float)border;
+
+  // TMA-staged path: f32 C1, 16-byte aligned source, bounding box small enough for shared memory
+  if (src.v.depth == RCV_F32 && src.v.cn == 1 && src.v.rows > 0 && src.v.cols > 0 &&
+      ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 15) == 0) && opt_get("warp.force_generic", 0) == 0) {
+    const double dxw = fabs(iM[0]) * (kWarpTW - 1) + fabs(iM[1]) * (kWarpTH - 1);
+    const double dyh = fabs(iM[3]) * (kWarpTW - 1) + fabs(iM[4]) * (kWarpTH - 1);
+    if (dxw < 250.0 && dyh < 250.0) {
+      WarpTileArgs t;
+      t.a = a;
+      t.d0 = iM[0];
+      t.d3 = iM[3];
+      const int al = (int)opt_get("warp.box_align", 4);
+      t.xalign = (int)opt_get("warp.x_align", 4);
+      t.bw = (((int)ceil(dxw) + 4 + (t.xalign - 1)) + al - 1) / al * al;
+      t.bh = (int)ceil(dyh) + 4;
+      const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16;  // tile + mbarrier
+      dim3 grid(ceil_div(a.dcols, kWarpTW), ceil_div(a.drows, kWarpTH), src.n);
+      if (t.bw <= 256 && t.bh <= 256 && smem <= 96 * 1024 && grid.y <= 65535) {
+        CUtensorMap tmap;
+        RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n,
+                                   src.frame_stride, t.bw, t.bh));
+        RCV_CUDA(cudaFuncSetAttribute(k_warp_f32_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_warp_f32_tile<<<grid, kWarpThreads, smem, s>>>(tmap, t);
+        count_launch();
+        RCV_CUDA(cudaGetLastError());
+        return RCV_OK;
+      }
+    }
+  }
+
   dim3 block(32, 8, 1);
   dim3 grid(ceil_div(a.dcols, 32), ceil_div(a.drows, 8), src.n);
   if (grid.y > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall");

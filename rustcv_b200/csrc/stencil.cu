@@ -24,65 +24,9 @@
 //   * BORDER_REFLECT_101 is produced by patching the landed tile in shared memory
 //     (TMA out-of-bounds fill is zeros), only in edge strips/bands.
 #include "rcv_internal.cuh"
+#include "tma_ptx.cuh"
 
 namespace rcv {
-
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a pipeline bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------
 // strip geometry
@@ -240,13 +184,14 @@ struct Gauss5Op {
 // ---------------------------------------------------------------------------------------
 // Op: Sobel 3x3 on single-channel f32 + magnitude.  Operation order is the oracle's
 // (orc_sobel3_f32): every op a single rounded f32 op, no fma.
-// out[0] = mag, out[1] = gx, out[2] = gy (each optional).
+// out[0] = mag; ALL = true adds out[1] = gx, out[2] = gy (each optional).
 // ---------------------------------------------------------------------------------------
+template <bool ALL>
 struct Sobel3Op {
   static constexpr int HV = 1;
   static constexpr int P = 1;
   static constexpr int E = 4;
-  static constexpr int NOUT = 3;
+  static constexpr int NOUT = ALL ? 3 : 1;
   float win[2][4];
 
   __device__ __forceinline__ void reset() {
@@ -286,15 +231,20 @@ struct Sobel3Op {
       float yy = __fmul_rn(gy[c], gy[c]);
       mg[c] = __fsqrt_rn(__fadd_rn(xx, yy));
     }
-    store4(outp[0], mg, nvalid, vec);
-    store4(outp[1], gx, nvalid, vec);
-    store4(outp[2], gy, nvalid, vec);
+    store4<FAST>(outp[0], mg, nvalid, vec);
+    if (ALL) {
+      store4<FAST>(outp[1], gx, nvalid, vec);
+      store4<FAST>(outp[2], gy, nvalid, vec);
+    }
   }
 
+  template <bool FAST>
   static __device__ __forceinline__ void store4(uint8_t *op, const float (&v)[4], int nvalid, bool vec) {
     float *o = (float *)op;
-    if (!o) return;
-    if (nvalid == 16 && vec) {
+    if (ALL && !o) return;
+    if (FAST) {
+      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid == 16 && vec) {
       *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
     } else if (nvalid > 0) {
 #pragma unroll
@@ -442,7 +392,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
           if ((j & 3) == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
 #pragma unroll
           for (int k = 0; k < Op::NOUT; ++k)
-            if (optr[k]) optr[k] += p.out[k].step;
+            if (Op::NOUT == 1 || optr[k]) optr[k] += p.out[k].step;
         }
         continue;
       }
@@ -570,7 +520,9 @@ int launch_sobel_strip(Ctx *c, const DBatch &src, const DBatch &mag, const DBatc
                        cudaStream_t s) {
   if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1) return RCV_ERR_UNSUPPORTED;
   DBatch outs[3] = {mag, gx, gy};
-  return launch_strip<Sobel3Op>(c, src, outs, 3, "sobel.band_rows", s);
+  if (!mag.v.data) return RCV_ERR_UNSUPPORTED;  // gx/gy without the magnitude: generic kernel
+  if (!gx.v.data && !gy.v.data) return launch_strip<Sobel3Op<false>>(c, src, outs, 1, "sobel.band_rows", s);
+  return launch_strip<Sobel3Op<true>>(c, src, outs, 3, "sobel.band_rows", s);
 }
 
 }  // namespace rcv
