@@ -286,14 +286,58 @@ struct WarpTileArgs {
   WarpArgs a;
   double d0, d3;  // iM[0], iM[3] in f64 for the tile's bounding box
   int bw, bh;     // box size in pixels
-  int xalign;     // box x origin is a multiple of this many pixels (power of two)
 };
+
+// One pixel.  INTERIOR: the whole box lies inside the image, so every tap is in-image and
+// inside the box -- no predicates at all.  Same operations in the same order either way.
+template <bool INTERIOR>
+__device__ __forceinline__ float warp_pixel(const WarpTileArgs &t, uint32_t tile, int bx0, int by0, float sx, float sy,
+                                            const uint8_t *src) {
+  const WarpArgs &a = t.a;
+  const float flx = floorf(sx), fly = floorf(sy);
+  const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
+  float p00, p01, p10, p11;
+  if (INTERIOR) {
+    const int cx = (int)flx - bx0, cy = (int)fly - by0;
+    const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
+    p00 = lds_f32(p);
+    p01 = lds_f32(p + 4);
+    p10 = lds_f32(p + t.bw * 4);
+    p11 = lds_f32(p + t.bw * 4 + 4);
+  } else {
+    const bool inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
+    const int ix = inside ? (int)flx : 0, iy = inside ? (int)fly : 0;
+    const bool x0ok = inside && ix >= 0, x1ok = inside && ix + 1 < a.scols;
+    const bool y0ok = inside && iy >= 0, y1ok = inside && iy + 1 < a.srows;
+    const int cx = ix - bx0, cy = iy - by0;  // tap (0,0) inside the box
+    const bool inbox = (unsigned)cx < (unsigned)(t.bw - 1) && (unsigned)cy < (unsigned)(t.bh - 1);
+    p00 = p01 = p10 = p11 = a.border;
+    if (inbox) {
+      const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
+      const float v00 = lds_f32(p), v01 = lds_f32(p + 4), v10 = lds_f32(p + t.bw * 4), v11 = lds_f32(p + t.bw * 4 + 4);
+      if (y0ok && x0ok) p00 = v00;
+      if (y0ok && x1ok) p01 = v01;
+      if (y1ok && x0ok) p10 = v10;
+      if (y1ok && x1ok) p11 = v11;
+    } else if (inside) {  // cannot happen for sane boxes; keeps the result exact regardless
+      const float *r0 = (const float *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
+      const float *r1 = (const float *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
+      if (y0ok && x0ok) p00 = __ldg(r0 + ix);
+      if (y0ok && x1ok) p01 = __ldg(r0 + ix + 1);
+      if (y1ok && x0ok) p10 = __ldg(r1 + ix);
+      if (y1ok && x1ok) p11 = __ldg(r1 + ix + 1);
+    }
+  }
+  const float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
+  const float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
+  return fmaf(fy, __fsub_rn(q1, q0), q0);
+}
 
 __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_constant__ CUtensorMap tmap,
                                                                 const WarpTileArgs t) {
   // no static shared memory in this kernel: the TMA destination must be 128-byte aligned and the
-  // dynamic segment only starts at offset 0 when nothing static precedes it.  The mbarrier lives
-  // behind the tile.
+  // dynamic segment only starts at offset 0 when nothing static precedes it.  Layout:
+  // [tile bw*bh floats][mbarrier, 16 B][row terms: TH x (bx, by) floats]
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const WarpArgs &a = t.a;
   const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * kWarpTH;
@@ -313,8 +357,10 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
   minx = fmin(fmax(minx, -1.0e6), 1.0e6 + a.scols);
   miny = fmin(fmax(miny, -1.0e6), 1.0e6 + a.srows);
   // the box starts on a 16-byte boundary of the row (4 floats): TMA rejects other inner offsets
-  const int bx0 = ((int)floor(minx) - 1) & ~(t.xalign - 1), by0 = (int)floor(miny) - 1;
-  const uint32_t tile = smem_u32(smem_raw), barp = tile + (((uint32_t)(t.bw * t.bh * 4) + 15u) & ~15u);
+  const int bx0 = ((int)floor(minx) - 1) & ~3, by0 = (int)floor(miny) - 1;
+  const uint32_t tile = smem_u32(smem_raw);
+  const uint32_t barp = tile + (((uint32_t)(t.bw * t.bh * 4) + 15u) & ~15u);
+  const uint32_t rowtab = barp + 16;
   if (threadIdx.x == 0) {
     mbar_init(barp, 1);
     fence_mbar_init();
@@ -322,50 +368,40 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
     mbar_expect_tx(barp, (uint32_t)(t.bw * t.bh * 4));
     tma_load_3d(tile, &tmap, barp, bx0, by0, (int)blockIdx.z);
   }
-  __syncthreads();  // barrier init visible to all waiters
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kWarpTH) {
+    // row terms, once per tile row: bx = (float)(iM[1]*y + iM[2]) -- f64 mul, f64 add, one rounding
+    const int r = threadIdx.x - 32;
+    const double y = (double)(ty0 + r);
+    const float bx = __double2float_rn(__dadd_rn(__dmul_rn(a.m1, y), a.m2));
+    const float by = __double2float_rn(__dadd_rn(__dmul_rn(a.m4, y), a.m5));
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(rowtab + r * 8), "f"(bx), "f"(by) : "memory");
+  }
+  __syncthreads();  // barrier init and row terms visible
   const int lx = threadIdx.x & 63, ly0 = threadIdx.x >> 6;
   const int x = tx0 + lx;
+  const float xf = (float)x;
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
-  bool waited = false;
+  float *drow = (float *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)(ty0 + ly0) * a.dstep) + x;
+  const bool interior = bx0 >= 0 && by0 >= 0 && bx0 + t.bw <= a.scols && by0 + t.bh <= a.srows;
+  const bool full = tx0 + kWarpTW <= a.dcols && ty0 + kWarpTH <= a.drows;
+  mbar_wait(barp, 0);
+  if (interior && full) {
+#pragma unroll
+    for (int k = 0; k < kWarpTH / 4; ++k) {
+      float bx, by;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
+      const float v = warp_pixel<true>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src);
+      *(float *)((uint8_t *)drow + (size_t)(4 * k) * a.dstep) = v;
+    }
+  } else {
 #pragma unroll 2
-  for (int k = 0; k < kWarpTH / 4; ++k) {
-    const int y = ty0 + ly0 + 4 * k;
-    const float bx = __double2float_rn(__dadd_rn(__dmul_rn(a.m1, (double)y), a.m2));
-    const float by = __double2float_rn(__dadd_rn(__dmul_rn(a.m4, (double)y), a.m5));
-    const float sx = fmaf(a.m0, (float)x, bx);
-    const float sy = fmaf(a.m3, (float)x, by);
-    const float flx = floorf(sx), fly = floorf(sy);
-    const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
-    const bool inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
-    const int ix = inside ? (int)flx : 0, iy = inside ? (int)fly : 0;
-    const bool x0ok = inside && ix >= 0, x1ok = inside && ix + 1 < a.scols;
-    const bool y0ok = inside && iy >= 0, y1ok = inside && iy + 1 < a.srows;
-    if (!waited) {
-      mbar_wait(barp, 0);
-      waited = true;
+    for (int k = 0; k < kWarpTH / 4; ++k) {
+      const int y = ty0 + ly0 + 4 * k;
+      float bx, by;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
+      const float v = warp_pixel<false>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src);
+      if (x < a.dcols && y < a.drows) *(float *)((uint8_t *)drow + (size_t)(4 * k) * a.dstep) = v;
     }
-    const int cx = ix - bx0, cy = iy - by0;  // tap (0,0) inside the box
-    const bool inbox = (unsigned)cx < (unsigned)(t.bw - 1) && (unsigned)cy < (unsigned)(t.bh - 1);
-    float p00 = a.border, p01 = a.border, p10 = a.border, p11 = a.border;
-    if (inbox) {
-      const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
-      const float v00 = lds_f32(p), v01 = lds_f32(p + 4), v10 = lds_f32(p + t.bw * 4), v11 = lds_f32(p + t.bw * 4 + 4);
-      if (y0ok && x0ok) p00 = v00;
-      if (y0ok && x1ok) p01 = v01;
-      if (y1ok && x0ok) p10 = v10;
-      if (y1ok && x1ok) p11 = v11;
-    } else if (inside) {  // cannot happen for sane boxes; keeps the result exact regardless
-      const float *r0 = (const float *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
-      const float *r1 = (const float *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
-      if (y0ok && x0ok) p00 = __ldg(r0 + ix);
-      if (y0ok && x1ok) p01 = __ldg(r0 + ix + 1);
-      if (y1ok && x0ok) p10 = __ldg(r1 + ix);
-      if (y1ok && x1ok) p11 = __ldg(r1 + ix + 1);
-    }
-    const float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
-    const float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
-    const float v = fmaf(fy, __fsub_rn(q1, q0), q0);
-    if (x < a.dcols && y < a.drows) ((float *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)y * a.dstep))[x] = v;
   }
 }
 
@@ -403,11 +439,12 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
       t.a = a;
       t.d0 = iM[0];
       t.d3 = iM[3];
-      const int al = (int)opt_get("warp.box_align", 4);
-      t.xalign = (int)opt_get("warp.x_align", 4);
-      t.bw = (((int)ceil(dxw) + 4 + (t.xalign - 1)) + al - 1) / al * al;
+      // +3: the box origin is floored to a multiple of 4 pixels.  Width = 16 (mod 32) floats keeps the
+      // rotated gather (a lane step of ~(cos, -sin) pixels) spread over the shared-memory banks.
+      t.bw = ((int)ceil(dxw) + 4 + 3 + 15) & ~15;
+      if ((t.bw & 31) == 0) t.bw += 16;
       t.bh = (int)ceil(dyh) + 4;
-      const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16;  // tile + mbarrier
+      const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16 + kWarpTH * 8;  // tile + mbarrier + row terms
       dim3 grid(ceil_div(a.dcols, kWarpTW), ceil_div(a.drows, kWarpTH), src.n);
       if (t.bw <= 256 && t.bh <= 256 && smem <= 96 * 1024 && grid.y <= 65535) {
         CUtensorMap tmap;
