@@ -92,6 +92,41 @@ __global__ void __launch_bounds__(256) k_cvt_scalar(CvtArgs a) {
 // byte k of a little-endian word array
 __device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu; }
 
+// ---- BT.601 for the vector kernel ----------------------------------------------------------
+// The reference formula (videoio/mod.rs:352-369) per channel is clamp((298*c + k1*u + k2*v + 128) >> 8)
+// with c = y-16, u = U-128, v = V-128.  Folding the offsets into one constant per channel gives
+//   B = 298*y + 516*U - 70688      G = 298*y - 100*U - 208*V + 34784      R = 298*y + 409*V - 56992
+// (all exact in i32): 2 IMAD for the luma terms, 4 for the chroma terms shared by both pixels,
+// 6 adds.  clamp(x >> 8) equals byte 1 of min(max(x, 0), 65535) (x < 0 -> 0; x >= 65536 -> 0xFFFF
+// -> 255; else floor(x / 256)), so shift + clamp is ONE VIMNMX.RELU (__vimin_s32_relu) and the
+// result bytes are gathered with PRMT (dp2a / cvt.pack are emulated on sm_100a -- measured slower).
+struct Px6 {
+  uint32_t b0, g0, r0, b1, g1, r1;  // clamped to [0, 65535]; the channel value is byte 1
+};
+
+template <bool UYVY>
+__device__ __forceinline__ Px6 yuv_word(uint32_t w) {
+  const int y0 = (int)__byte_perm(w, 0, UYVY ? 0x4441 : 0x4440);
+  const int u = (int)__byte_perm(w, 0, UYVY ? 0x4440 : 0x4441);
+  const int y1 = (int)__byte_perm(w, 0, UYVY ? 0x4443 : 0x4442);
+  const int v = (int)__byte_perm(w, 0, UYVY ? 0x4442 : 0x4443);
+  const int cy0 = y0 * 298, cy1 = y1 * 298;
+  const int db = u * 516 - 70688;
+  const int dr = v * 409 - 56992;
+  const int dg = u * -100 + (v * -208 + 34784);
+  Px6 o;
+  o.b0 = (uint32_t)__vimin_s32_relu(cy0 + db, 65535);
+  o.g0 = (uint32_t)__vimin_s32_relu(cy0 + dg, 65535);
+  o.r0 = (uint32_t)__vimin_s32_relu(cy0 + dr, 65535);
+  o.b1 = (uint32_t)__vimin_s32_relu(cy1 + db, 65535);
+  o.g1 = (uint32_t)__vimin_s32_relu(cy1 + dg, 65535);
+  o.r1 = (uint32_t)__vimin_s32_relu(cy1 + dr, 65535);
+  return o;
+}
+
+// {lo16(a), lo16(b)} as one register
+__device__ __forceinline__ uint32_t pair16(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }
+
 // YUYV/UYVY -> BGR: a thread converts 8 macro-pixels: 32 B in (2 x LDG.128) -> 48 B out (3 x STG.128).
 // -> GRAY: 16 px -> 16 B out.
 template <int CODE>
@@ -106,35 +141,32 @@ __global__ void __launch_bounds__(128) k_yuv422_vec(CvtArgs a) {
     uint4 q0 = __ldg((const uint4 *)(s + (size_t)g * 32));
     uint4 q1 = __ldg((const uint4 *)(s + (size_t)g * 32 + 16));
     uint32_t in[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    uint32_t out[12];
-    uint32_t gr[4];
-    uint8_t ob[48];
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      uint32_t w = in[p];
-      int b0 = w & 0xFF, b1 = (w >> 8) & 0xFF, b2 = (w >> 16) & 0xFF, b3 = w >> 24;
-      Bgr2 o = (CODE == RCV_COLOR_UYVY2BGR) ? yuv_pair(b1, b0, b3, b2) : yuv_pair(b0, b1, b2, b3);
-      if (CODE == RCV_COLOR_YUYV2GRAY) {
-        ob[p * 2] = (uint8_t)gray_of(o.b0, o.g0, o.r0);
-        ob[p * 2 + 1] = (uint8_t)gray_of(o.b1, o.g1, o.r1);
-      } else {
-        ob[p * 6 + 0] = (uint8_t)o.b0;
-        ob[p * 6 + 1] = (uint8_t)o.g0;
-        ob[p * 6 + 2] = (uint8_t)o.r0;
-        ob[p * 6 + 3] = (uint8_t)o.b1;
-        ob[p * 6 + 4] = (uint8_t)o.g1;
-        ob[p * 6 + 5] = (uint8_t)o.r1;
-      }
-    }
     if (CODE == RCV_COLOR_YUYV2GRAY) {
+      uint32_t gr[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        gr[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | ((uint32_t)ob[4 * k + 3] << 24);
+      for (int k = 0; k < 4; ++k) {
+        uint32_t gy[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          Px6 o = yuv_word<false>(in[2 * k + h]);
+          gy[2 * h] = gray_of(o.b0 >> 8, o.g0 >> 8, o.r0 >> 8);
+          gy[2 * h + 1] = gray_of(o.b1 >> 8, o.g1 >> 8, o.r1 >> 8);
+        }
+        gr[k] = gy[0] | (gy[1] << 8) | (gy[2] << 16) | (gy[3] << 24);
+      }
       *(uint4 *)(d + (size_t)g * 16) = make_uint4(gr[0], gr[1], gr[2], gr[3]);
     } else {
+      uint32_t out[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k)
-        out[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | ((uint32_t)ob[4 * k + 3] << 24);
+      for (int k = 0; k < 4; ++k) {  // two macro-pixels -> 12 bytes = 3 words
+        Px6 a0 = yuv_word<CODE == RCV_COLOR_UYVY2BGR>(in[2 * k]);
+        Px6 a1 = yuv_word<CODE == RCV_COLOR_UYVY2BGR>(in[2 * k + 1]);
+        uint32_t p0 = pair16(a0.b0, a0.g0), p1 = pair16(a0.r0, a0.b1), p2 = pair16(a0.g1, a0.r1);
+        uint32_t p3 = pair16(a1.b0, a1.g0), p4 = pair16(a1.r0, a1.b1), p5 = pair16(a1.g1, a1.r1);
+        out[3 * k] = __byte_perm(p0, p1, 0x7531);      // B0 G0 R0 B1
+        out[3 * k + 1] = __byte_perm(p2, p3, 0x7531);  // G1 R1 B0' G0'
+        out[3 * k + 2] = __byte_perm(p4, p5, 0x7531);  // R0' B1' G1' R1'
+      }
       uint4 *dp = (uint4 *)(d + (size_t)g * 48);
       dp[0] = make_uint4(out[0], out[1], out[2], out[3]);
       dp[1] = make_uint4(out[4], out[5], out[6], out[7]);
