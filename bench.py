@@ -204,6 +204,43 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pins this rank to the CPUs local to its GPU (sysfs local_cpulist) BEFORE any pinned host
+    memory is allocated, so the staging buffers are first-touched on the GPU's own NUMA node."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local).pci_bus_id  # type: ignore[attr-defined]
+    except Exception:
+        try:
+            out = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                          text=True).strip()
+            bus = out
+        except Exception as e:  # noqa: BLE001
+            return f"unbound ({e})"
+    try:
+        if isinstance(bus, int):
+            return "unbound (no bus id string)"
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit domain
+            bus = bus[4:]
+        path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"bound to {len(allowed)} CPUs local to {bus}"
+        return "unbound (no overlap with the allowed CPU set)"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({e})"
+
+
 # ---- GPU arm ---------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -230,6 +267,7 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: rustcv_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -263,15 +301,15 @@ def main() -> None:
     def step():
         R.imgproc.gaussian_blur_batch(src, dst, (5, 5), 0.0, 0.0)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     R.imgproc.sync(local)
     torch.cuda.synchronize()
     barrier()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = R.imgproc.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -285,7 +323,6 @@ def main() -> None:
     ms_local = e0.elapsed_time(e1)
     barrier()
     ms = reduce_max(ms_local, device=dev)
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     total_pix = reduce_sum(float(F_ * PIX), device=dev)  # pixels per step over all ranks
     value = total_pix / (ms_per_step * 1e-3) / 1e6
@@ -319,6 +356,7 @@ def main() -> None:
     e2e_s = reduce_max(e2e_s_local, device=dev)
     e2e_pix = reduce_sum(float(E * PIX), device=dev)
     e2e_value = e2e_pix * args.steps / e2e_s / 1e6
+    clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up through both timed regions
     e2e_ok = None
     if rank == 0:
         e2e_ok = O.crc32(hdst[0].to_numpy()) == 0x827081C8
@@ -350,7 +388,7 @@ def main() -> None:
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * F_ * PIX},
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": E * PIX * CN * world,
                     "d2h_bytes_per_step": E * PIX * CN * world, "frames_per_gpu_per_step": E,
-                    "api": "rcv_gaussian_blur_batch on pinned host Mats"},
+                    "api": "rcv_gaussian_blur_batch on pinned host Mats", "host_binding": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": {"device_frame0_crc_827081c8": crc_ok, "e2e_frame0_crc_827081c8": e2e_ok},

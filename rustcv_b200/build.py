@@ -14,8 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "librcv_imgproc.so")
-SOURCES = ["context.cu", "tma.cu", "cvt.cu", "stencil.cu", "filter.cu", "geom.cu", "abi.cu"]
-HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(HERE, "..", "include", "rcv_imgproc.h")]
+SOURCES = ["context.cu", "tma.cu", "cvt.cu", "strip_gauss5.cu", "strip_gaussq8_k3.cu", "strip_gaussq8_k5.cu", "strip_gaussq8_k7.cu", "strip_sobel.cu", "filter.cu", "geom.cu", "abi.cu"]
+HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(CSRC, "strip_pipeline.cuh"),
+           os.path.join(CSRC, "strip_gaussq8.cuh"), os.path.join(HERE, "..", "include", "rcv_imgproc.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the f32 specs fix where fused multiply-adds happen (explicit fmaf only).
@@ -51,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl"]

@@ -200,6 +200,8 @@ void gaussian_kernel_q8(int n, double sigma, int32_t *kq) {
 }
 
 int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_gaussq8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, const int32_t *ky, int ks,
+                         cudaStream_t s);
 
 int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh, double sx, double sy,
                     cudaStream_t s) {
@@ -217,6 +219,10 @@ int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh
                            ky[1] == 64 && ky[2] == 96;
     if (binomial5 && opt_get("gauss.force_generic", 0) == 0) {
       int rc = launch_gauss5_strip(c, src, dst, s);
+      if (rc != RCV_ERR_UNSUPPORTED) return rc;
+    }
+    if (kw == kh && (kw == 3 || kw == 5 || kw == 7) && opt_get("gauss.force_generic", 0) == 0) {
+      int rc = launch_gaussq8_strip(c, src, dst, kx, ky, kw, s);
       if (rc != RCV_ERR_UNSUPPORTED) return rc;
     }
     return launch_sepfilter_q8(c, src, dst, kx, kw, ky, kh, s);

@@ -4,7 +4,7 @@
 //   context.cu   per-GPU context, streams, staging rings, device Mats, options
 //   tma.cu       cuTensorMapEncodeTiled plumbing (driver entry point, no -lcuda)
 //   cvt.cu       pixel-format conversion kernels     (videoio/mod.rs:344-399)
-//   stencil.cu   TMA strip-pipeline kernels: binomial Gaussian u8, Sobel f32
+//   strip_*.cu   TMA strip-pipeline kernels (strip_pipeline.cuh): Gaussian u8, Sobel f32
 //   filter.cu    generic separable / dense filters (u8 Q8, f32)
 //   geom.cu      bilinear resize, warpAffine
 //   abi.cu       the extern "C" entry points of include/rcv_imgproc.h

@@ -23,6 +23,8 @@
 //     byte gathers.
 //   * BORDER_REFLECT_101 is produced by patching the landed tile in shared memory
 //     (TMA out-of-bounds fill is zeros), only in edge strips/bands.
+#pragma once
+
 #include "rcv_internal.cuh"
 #include "tma_ptx.cuh"
 
@@ -49,209 +51,7 @@ struct StripParams {
   int vec_store;  // all outputs 16-byte aligned (base, step, frame stride)
   long long total_items;
   unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
-};
-
-// ---------------------------------------------------------------------------------------
-// Op: 5x5 binomial Gaussian on u8, CN interleaved channels.
-//   out = (sum_ij k_i k_j p + 128) >> 8, k = {1,4,6,4,1}   (oracle: orc_sepfilter_u8_q8
-//   with Q8 taps {16,64,96,64,16}: (sum ky kx p + 32768) >> 16 is the same number)
-// ---------------------------------------------------------------------------------------
-// Integer ops pinned with inline PTX so that NVVM cannot re-associate the sums (it turns
-// the 4-op forms below into 5): ptxas still picks the pipe (IADD3 / IMAD.IADD / LEA).
-__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-template <int M>
-__device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
-  uint32_t d;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(M), "r"(c));
-  return d;
-}
-
-template <int CN>
-struct Gauss5Op {
-  static constexpr int HV = 2;   // rows of vertical halo
-  static constexpr int P = 2;    // pixels of horizontal halo
-  static constexpr int E = CN;   // bytes per pixel
-  static constexpr int NOUT = 1;
-  uint32_t win[4][8];  // last 4 rows, unpacked: [2w] = bytes 0,2 of word w; [2w+1] = bytes 1,3
-
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) win[j][h] = 0;
-  }
-
-  // J = (feed index) & 3, compile time: win[J] holds the oldest row.
-  // FAST: interior rows of an aligned, non-ragged strip -- always emits, lanes store 16 B or nothing.
-  template <int J, bool FAST>
-  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    uint32_t in[8];
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      in[2 * k] = __byte_perm(w[k], 0, 0x4240);      // (b0, b2) as 16-bit lanes
-      in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);  // (b1, b3)
-    }
-    // vertical: V = r0 + 4 r1 + 6 r2 + 4 r3 + r4 (+8 per lane: with horizontal taps summing
-    // to 16 that is the final "+128" rounding term).  V <= 4088 per 16-bit lane.
-    uint32_t V[8];
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      const uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
-      const uint32_t a = add3(r0, in[h], 0x00080008u);
-      const uint32_t b = add2(r1, r3);
-      V[h] = madc<6>(r2, madc<4>(b, a));
-      win[J][h] = in[h];
-    }
-    if (!FAST && !emit) return;
-
-    // Vertical sums of words -2..5 (index +2) as lo = (byte0, byte2) / hi = (byte1, byte3) pairs and
-    // the odd-phase pairs S[i] = (byte 2|3 of word i, byte 0|1 of word i+1).  Own words 0..3; the
-    // neighbours' by shuffle: from the left lane its word 3 and its S of words 2-3, from the right
-    // lane its word 0 and its S of words 0-1.
-    uint32_t lo[8], hi[8], loS[7], hiS[7];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      lo[k + 2] = V[2 * k];
-      hi[k + 2] = V[2 * k + 1];
-    }
-#pragma unroll
-    for (int i = 2; i < 5; ++i) {
-      loS[i] = __byte_perm(lo[i], lo[i + 1], 0x5432);
-      hiS[i] = __byte_perm(hi[i], hi[i + 1], 0x5432);
-    }
-    lo[1] = __shfl_up_sync(0xffffffffu, lo[5], 1);
-    hi[1] = __shfl_up_sync(0xffffffffu, hi[5], 1);
-    loS[0] = __shfl_up_sync(0xffffffffu, loS[4], 1);
-    hiS[0] = __shfl_up_sync(0xffffffffu, hiS[4], 1);
-    lo[6] = __shfl_down_sync(0xffffffffu, lo[2], 1);
-    hi[6] = __shfl_down_sync(0xffffffffu, hi[2], 1);
-    loS[6] = __shfl_down_sync(0xffffffffu, loS[2], 1);
-    hiS[6] = __shfl_down_sync(0xffffffffu, hiS[2], 1);
-    loS[1] = __byte_perm(lo[1], lo[2], 0x5432);
-    hiS[1] = __byte_perm(hi[1], hi[2], 0x5432);
-    loS[5] = __byte_perm(lo[5], lo[6], 0x5432);
-    hiS[5] = __byte_perm(hi[5], hi[6], 0x5432);
-    if constexpr (CN == 4) {  // taps at -8 / +8 bytes land on whole words -2 and 5
-      lo[0] = __shfl_up_sync(0xffffffffu, lo[4], 1);
-      hi[0] = __shfl_up_sync(0xffffffffu, hi[4], 1);
-      lo[7] = __shfl_down_sync(0xffffffffu, lo[3], 1);
-      hi[7] = __shfl_down_sync(0xffffffffu, hi[3], 1);
-    } else {
-      lo[0] = hi[0] = lo[7] = hi[7] = 0;  // never selected: CN <= 3 reaches words -2 / 5 only through S[0] / S[6]
-    }
-
-    uint32_t ow[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t H[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        uint32_t t[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int p = 4 * k + e + (j - 2) * CN + 8;  // byte position relative to word -2
-          const int wd = p >> 2, ph = p & 3;
-          t[j] = ph == 0 ? lo[wd] : ph == 1 ? hi[wd] : ph == 2 ? loS[wd] : hiS[wd];
-        }
-        H[e] = madc<6>(t[2], madc<4>(add2(t[1], t[3]), add2(t[0], t[4])));  // <= 16 * 4088 = 65408 per lane
-      }
-      ow[k] = __byte_perm(H[0], H[1], 0x7351);  // high bytes of the four 16-bit lanes, in byte order
-    }
-    uint8_t *o = outp[0];
-    if (FAST) {
-      if (nvalid == 16) *(uint4 *)o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    } else if (nvalid == 16 && vec) {
-      *(uint4 *)o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    } else if (nvalid > 0) {  // ragged right edge / unaligned dst only; halo lanes store nothing
-#pragma unroll
-      for (int b = 0; b < 16; ++b)
-        if (b < nvalid) o[b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
-    }
-  }
-  static_assert(CN >= 1 && CN <= 4, "the farthest taps (2*CN bytes) must stay within two words");
-};
-
-// ---------------------------------------------------------------------------------------
-// Op: Sobel 3x3 on single-channel f32 + magnitude.  Operation order is the oracle's
-// (orc_sobel3_f32): every op a single rounded f32 op, no fma.
-// out[0] = mag; ALL = true adds out[1] = gx, out[2] = gy (each optional).
-// ---------------------------------------------------------------------------------------
-template <bool ALL>
-struct Sobel3Op {
-  static constexpr int HV = 1;
-  static constexpr int P = 1;
-  static constexpr int E = 4;
-  static constexpr int NOUT = ALL ? 3 : 1;
-  float win[2][4];
-
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int h = 0; h < 4; ++h) win[j][h] = 0.0f;
-  }
-
-  template <int J, bool FAST>
-  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    constexpr int JJ = J & 1;
-    const float pp[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
-    float s[6], d[6];  // columns -1..4 at index +1
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float pm = win[JJ][c], p0 = win[JJ ^ 1][c];
-      float t = __fadd_rn(pm, pp[c]);
-      float u = __fmul_rn(2.0f, p0);
-      s[c + 1] = __fadd_rn(t, u);
-      d[c + 1] = __fsub_rn(pp[c], pm);
-      win[JJ][c] = pp[c];
-    }
-    if (!FAST && !emit) return;
-    s[0] = __shfl_up_sync(0xffffffffu, s[4], 1);
-    d[0] = __shfl_up_sync(0xffffffffu, d[4], 1);
-    s[5] = __shfl_down_sync(0xffffffffu, s[1], 1);
-    d[5] = __shfl_down_sync(0xffffffffu, d[1], 1);
-    float gx[4], gy[4], mg[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      gx[c] = __fsub_rn(s[c + 2], s[c]);
-      float t = __fadd_rn(d[c], d[c + 2]);
-      float u = __fmul_rn(2.0f, d[c + 1]);
-      gy[c] = __fadd_rn(t, u);
-      float xx = __fmul_rn(gx[c], gx[c]);
-      float yy = __fmul_rn(gy[c], gy[c]);
-      mg[c] = __fsqrt_rn(__fadd_rn(xx, yy));
-    }
-    store4<FAST>(outp[0], mg, nvalid, vec);
-    if (ALL) {
-      store4<FAST>(outp[1], gx, nvalid, vec);
-      store4<FAST>(outp[2], gy, nvalid, vec);
-    }
-  }
-
-  template <bool FAST>
-  static __device__ __forceinline__ void store4(uint8_t *op, const float (&v)[4], int nvalid, bool vec) {
-    float *o = (float *)op;
-    if (ALL && !o) return;
-    if (FAST) {
-      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (nvalid == 16 && vec) {
-      *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (nvalid > 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c * 4 < nvalid) o[c] = v[c];
-    }
-  }
+  uint32_t taps_x[4], taps_y[4];  // GaussQ8Op: symmetric Q8 taps, [0] outermost .. [KS/2] centre
 };
 
 // ---------------------------------------------------------------------------------------
@@ -259,7 +59,7 @@ struct Sobel3Op {
 // ---------------------------------------------------------------------------------------
 template <class Op, int R, int S, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CUtensorMap tmap, const StripParams p) {
-  static_assert(R % 4 == 0 && R >= 2 * Op::HV + 1 && R <= 32, "chunk rows");
+  static_assert(R == 8 && R >= 2 * Op::HV + 1, "chunk rows (the ops' window rotation assumes 8-row chunks)");
   static_assert(Op::E * (Op::P + 1) <= 16, "horizontal halo must fit the 16-byte halo lanes");
   constexpr int HV = Op::HV, P = Op::P, E = Op::E;
   constexpr uint32_t kStageBytes = R * kTileBytes;
@@ -280,6 +80,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   uint32_t phase = 0;  // bit s = parity the next wait on stage s must see
   const long long total_warps = (long long)gridDim.x * NW;
   Op op;
+  op.init(p);
 
   long long item = (long long)blockIdx.x * NW + warp;
   while (item < p.total_items) {
@@ -380,31 +181,43 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       if (lane == 0 && c >= 1 && c - 1 + S < n_chunks) issue(c - 1 + S);
 
       // ---- rows of this chunk ----
-      if (fast_strip && c * R >= 2 * HV && c * R + R <= n_feed) {
-        // interior chunk of an aligned, non-ragged strip: every row is fed and emitted, no per-row tests
+      if (fast_strip && c * R + R <= n_feed) {
+        // whole chunk of an aligned, non-ragged strip: every row is fed; every row emits except the
+        // first 2*HV rows of the band (chunk 0), which only fill the window.  No per-row tests.
         const uint32_t rowaddr = tile + lane * kLaneBytes;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const uint4 q = lds128(rowaddr + j * kTileBytes);
-          if ((j & 3) == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
-          if ((j & 3) == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
-          if ((j & 3) == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
-          if ((j & 3) == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
+          if (j < 2 * HV && c == 0) {
+            if (j == 0) op.template warm<0>(q);
+            if (j == 1) op.template warm<1>(q);
+            if (j == 2) op.template warm<2>(q);
+            if (j == 3) op.template warm<3>(q);
+            if (j == 4) op.template warm<4>(q);
+            if (j == 5) op.template warm<5>(q);
+            continue;
+          }
+          if (j == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
+          if (j == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
+          if (j == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
+          if (j == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
+          if (j == 4) op.template feed<4, true>(q, true, optr, nvalid, true);
+          if (j == 5) op.template feed<5, true>(q, true, optr, nvalid, true);
+          if (j == 6) op.template feed<6, true>(q, true, optr, nvalid, true);
+          if (j == 7) op.template feed<7, true>(q, true, optr, nvalid, true);
 #pragma unroll
           for (int k = 0; k < Op::NOUT; ++k)
             if (Op::NOUT == 1 || optr[k]) optr[k] += p.out[k].step;
         }
         continue;
       }
-#pragma unroll 1
-      for (int g = 0; g < R / 4; ++g) {
-        const int fi0 = c * R + g * 4;
-        if (fi0 >= n_feed) break;
-        const uint32_t rowaddr = tile + (uint32_t)(g * 4) * kTileBytes + lane * kLaneBytes;
+      // first / last chunks of a band, ragged or unaligned strips: per-row tests
+      {
+        const uint32_t rowaddr = tile + lane * kLaneBytes;
         // feed index fi produces output row y0 + fi - 2*HV
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int fi = fi0 + j;
+        for (int j = 0; j < R; ++j) {
+          const int fi = c * R + j;
           if (fi < n_feed) {
             const uint4 q = lds128(rowaddr + j * kTileBytes);
             const bool emit = fi >= 2 * HV;
@@ -412,6 +225,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
             if (j == 1) op.template feed<1, false>(q, emit, optr, nvalid, p.vec_store != 0);
             if (j == 2) op.template feed<2, false>(q, emit, optr, nvalid, p.vec_store != 0);
             if (j == 3) op.template feed<3, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 4) op.template feed<4, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 5) op.template feed<5, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 6) op.template feed<6, false>(q, emit, optr, nvalid, p.vec_store != 0);
+            if (j == 7) op.template feed<7, false>(q, emit, optr, nvalid, p.vec_store != 0);
             if (emit) {
 #pragma unroll
               for (int k = 0; k < Op::NOUT; ++k)
@@ -434,11 +251,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------
 constexpr int kR = 8, kS = 3, kNW = 16;
 
-static bool aligned16(const DBatch &b) {
+static inline bool aligned16(const DBatch &b) {
   return b.v.data && (((uintptr_t)b.v.data | b.v.step | b.frame_stride) & 15) == 0;
 }
 
-bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
+static inline bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
   return aligned16(src) && src.v.rows >= min_rows && src.v.cols >= min_cols;
 }
 
@@ -448,7 +265,7 @@ bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
 // tens of MB (TLB reach, L2-resident halo rows) instead of hundreds.  36 rows (40 fed rows =
 // 5 chunks of R) measured best for the 5x5 Gaussian: 8.04 us per 4K frame vs 8.64 at 60 rows
 // and 10.9 at 244.  Tiny jobs use shorter bands to occupy more warps.
-static int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv) {
+static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv) {
   int64_t forced = opt_get(optname, 0);
   if (forced > 0) return (int)forced;
   const long long warps = (long long)ctx_sm_count(c) * kNW;
@@ -460,7 +277,7 @@ static int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int
 
 template <class Op>
 static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout, const char *band_opt,
-                        cudaStream_t s) {
+                        cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr) {
   CUtensorMap tmap;
   RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
                              kTileBytes / 4, kR));
@@ -482,6 +299,10 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
   p.next_item = nullptr;
+  for (int i = 0; i < 4; ++i) {
+    p.taps_x[i] = taps_x ? (uint32_t)taps_x[i] : 0;
+    p.taps_y[i] = taps_y ? (uint32_t)taps_y[i] : 0;
+  }
 
   auto kern = k_strip<Op, kR, kS, kNW>;
   const int smem = kNW * kS * kR * kTileBytes + kNW * kS * 8;
@@ -500,29 +321,6 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;
-}
-
-// GaussianBlur 5x5 sigma=0 (binomial) fast path.  Returns RCV_ERR_UNSUPPORTED when the
-// geometry is not eligible; the caller then uses the generic separable kernel.
-int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
-  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_U8) return RCV_ERR_UNSUPPORTED;
-  if (src.v.row_bytes() > (size_t)1 << 30) return RCV_ERR_UNSUPPORTED;
-  switch (src.v.cn) {
-    case 1: return launch_strip<Gauss5Op<1>>(c, src, &dst, 1, "gauss.band_rows", s);
-    case 2: return launch_strip<Gauss5Op<2>>(c, src, &dst, 1, "gauss.band_rows", s);
-    case 3: return launch_strip<Gauss5Op<3>>(c, src, &dst, 1, "gauss.band_rows", s);
-    case 4: return launch_strip<Gauss5Op<4>>(c, src, &dst, 1, "gauss.band_rows", s);
-  }
-  return RCV_ERR_UNSUPPORTED;
-}
-
-int launch_sobel_strip(Ctx *c, const DBatch &src, const DBatch &mag, const DBatch &gx, const DBatch &gy,
-                       cudaStream_t s) {
-  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1) return RCV_ERR_UNSUPPORTED;
-  DBatch outs[3] = {mag, gx, gy};
-  if (!mag.v.data) return RCV_ERR_UNSUPPORTED;  // gx/gy without the magnitude: generic kernel
-  if (!gx.v.data && !gy.v.data) return launch_strip<Sobel3Op<false>>(c, src, outs, 1, "sobel.band_rows", s);
-  return launch_strip<Sobel3Op<true>>(c, src, outs, 3, "sobel.band_rows", s);
 }
 
 }  // namespace rcv

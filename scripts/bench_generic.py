@@ -1,0 +1,83 @@
+"""Device-resident timing of the general-case kernels (not BASELINE configs): GB/s of algorithmic
+traffic and fraction of the measured HBM peak.  GPU box only."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import rustcv_b200 as R  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
+from rustcv_b200 import _ffi as F  # noqa: E402
+
+PEAK = 6549.4
+R.imgproc.init(0)
+stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(0))
+R.imgproc.set_blocking(False)
+I = R.imgproc
+
+
+def dev(a):
+    h = R.Mat.from_numpy(a)
+    return h.upload()
+
+
+def timeit(fn, steps=10, warm=2):
+    for _ in range(warm):
+        fn()
+    I.sync(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    I.sync(0)
+    return e0.elapsed_time(e1) / steps
+
+
+def report(name, ms, nbytes):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"case": name, "ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+
+
+H, W = 2160, 3840
+bgr = dev(O.fill_u8(2, H * W * 3).reshape(H, W, 3))
+out3 = bgr.like()
+want = set(sys.argv[1:])
+
+
+def case(name):
+    return not want or name in want
+
+
+if case("gauss"):
+    for ks, sg in (((3, 3), 0.0), ((7, 7), 1.5), ((5, 5), 1.0), ((11, 11), 0.0)):
+        report(f"gauss u8c3 4K {ks} s{sg}", timeit(lambda: I.gaussian_blur(bgr, out3, ks, sg)), 6 * H * W)
+    f = dev(O.fill_f32(3, 1080 * 1920).reshape(1080, 1920))
+    fo = f.like()
+    report("gauss f32c1 1080p 5x5 s1.1", timeit(lambda: I.gaussian_blur(f, fo, (5, 5), 1.1)), 8 * 1080 * 1920)
+if case("filter2d"):
+    k = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
+    report("filter2d u8c3 4K 3x3", timeit(lambda: I.filter2d(bgr, out3, k)), 6 * H * W)
+    k5 = np.ones((5, 5), np.float32) / 25
+    report("filter2d u8c3 4K 5x5", timeit(lambda: I.filter2d(bgr, out3, k5)), 6 * H * W)
+if case("cvt"):
+    g = bgr.like(channels=1)
+    report("bgr2gray 4K", timeit(lambda: I.cvt_color(bgr, g, I.COLOR_BGR2GRAY)), 4 * H * W)
+    report("rgb2bgr 4K", timeit(lambda: I.cvt_color(bgr, out3, I.COLOR_RGB2BGR)), 6 * H * W)
+    x = bgr.like(channels=4)
+    report("bgr2xrgb32 4K", timeit(lambda: I.cvt_color(bgr, x, I.COLOR_BGR2XRGB32)), 7 * H * W)
+    report("bgra2bgr 4K", timeit(lambda: I.cvt_color(x, out3, I.COLOR_BGRA2BGR)), 7 * H * W)
+if case("resize"):
+    d = bgr.like(rows=720, cols=1280)
+    report("resize u8c3 4K->720p (3x, general)", timeit(lambda: I.resize(bgr, d)), 15 * 720 * 1280)
+    d2 = bgr.like(rows=1080, cols=1920)
+    report("resize u8c3 4K->1080p (2x, general)", timeit(lambda: I.resize(bgr, d2)), 15 * 1080 * 1920)
+    d3 = bgr.like(rows=4320, cols=7680)
+    report("resize u8c3 4K->8K (upscale)", timeit(lambda: I.resize(bgr, d3)), (3 * H * W + 3 * 4320 * 7680))
+if case("single"):
+    report("gauss5 single 4K frame (1 launch)", timeit(lambda: I.gaussian_blur(bgr, out3, (5, 5), 0.0), steps=50), 6 * H * W)

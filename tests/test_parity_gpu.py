@@ -260,6 +260,38 @@ def test_gaussian_general_taps_u8(rcv, oracle, ks, sigma):
     assert_same(d.to_numpy(), oracle.gaussian_blur(a, ks, float(sigma), float(sigma)), f"gauss {ks} {sigma}")
 
 
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("ks,sx,sy", [(3, 0.0, 0.0), (3, 0.6, 1.4), (5, 1.0, 1.0), (5, 0.7, 2.5), (7, 0.0, 0.0), (7, 1.5, 1.5),
+                                      (7, 3.0, 0.9)])
+def test_gaussian_q8_strip_kernel(rcv, oracle, cn, ks, sx, sy):
+    """k_strip<GaussQ8Op<CN, KS>>: any-sigma 3/5/7 Gaussians, multi-strip, ragged right edge, band seams."""
+    R = rcv
+    h, w = 203, 517
+    a = oracle.fill_u8(140 + cn + ks, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+    s = mats(R, a, "device")
+    d = s.like()
+    R.imgproc.gaussian_blur(s, d, (ks, ks), sx, sy)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(a, (ks, ks), sx, sy), f"gaussq8 cn{cn} ks{ks} {sx} {sy}")
+
+
+def test_gaussian_q8_extremes(rcv, oracle):
+    """All-255 and checkerboard inputs sit on the 16-bit lane bounds of the packed arithmetic."""
+    R = rcv
+    for ks, sg in ((3, 0.0), (5, 1.3), (7, 2.0)):
+        for a in (np.full((64, 200, 3), 255, np.uint8),
+                  ((np.indices((64, 200)).sum(0) % 2) * 255).astype(np.uint8)[:, :, None].repeat(3, 2)):
+            a = np.ascontiguousarray(a)
+            s = mats(R, a, "device")
+            d = s.like()
+            R.imgproc.gaussian_blur(s, d, (ks, ks), sg)
+            assert_same(d.to_numpy(), oracle.gaussian_blur(a, (ks, ks), sg, sg), f"extreme ks{ks}")
+    a = np.full((64, 200, 3), 255, np.uint8)
+    s = mats(R, a, "device")
+    d = s.like()
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    assert (d.to_numpy() == 255).all()
+
+
 def test_gaussian_strided_and_padding_untouched(rcv, oracle):
     """Mat.step > cols*channels on input AND output; padding bytes must survive."""
     R = rcv
