@@ -341,32 +341,33 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const WarpArgs &a = t.a;
   const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * kWarpTH;
-  // bounding box origin from the four tile corners (f64)
-  const double xs[2] = {(double)tx0, (double)(tx0 + kWarpTW - 1)}, ys[2] = {(double)ty0, (double)(ty0 + kWarpTH - 1)};
-  double minx = 1e300, miny = 1e300;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      double sx = t.d0 * xs[i] + a.m1 * ys[j] + a.m2;
-      double sy = t.d3 * xs[i] + a.m4 * ys[j] + a.m5;
-      minx = fmin(minx, sx);
-      miny = fmin(miny, sy);
-    }
-  // clamp far-out-of-image boxes so the int conversion and the TMA coordinates stay sane
-  minx = fmin(fmax(minx, -1.0e6), 1.0e6 + a.scols);
-  miny = fmin(fmax(miny, -1.0e6), 1.0e6 + a.srows);
-  // the box starts on a 16-byte boundary of the row (4 floats): TMA rejects other inner offsets
-  const int bx0 = ((int)floor(minx) - 1) & ~3, by0 = (int)floor(miny) - 1;
   const uint32_t tile = smem_u32(smem_raw);
   const uint32_t barp = tile + (((uint32_t)(t.bw * t.bh * 4) + 15u) & ~15u);
   const uint32_t rowtab = barp + 16;
   if (threadIdx.x == 0) {
+    // bounding box origin from the four tile corners (f64), once per tile
+    const double xs[2] = {(double)tx0, (double)(tx0 + kWarpTW - 1)}, ys[2] = {(double)ty0, (double)(ty0 + kWarpTH - 1)};
+    double minx = 1e300, miny = 1e300;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double sx = t.d0 * xs[i] + a.m1 * ys[j] + a.m2;
+        double sy = t.d3 * xs[i] + a.m4 * ys[j] + a.m5;
+        minx = fmin(minx, sx);
+        miny = fmin(miny, sy);
+      }
+    // clamp far-out-of-image boxes so the int conversion and the TMA coordinates stay sane
+    minx = fmin(fmax(minx, -1.0e6), 1.0e6 + a.scols);
+    miny = fmin(fmax(miny, -1.0e6), 1.0e6 + a.srows);
+    // the box starts on a 16-byte boundary of the row (4 floats): TMA rejects other inner offsets
+    const int ox = ((int)floor(minx) - 1) & ~3, oy = (int)floor(miny) - 1;
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(barp + 8), "r"(ox), "r"(oy) : "memory");
     mbar_init(barp, 1);
     fence_mbar_init();
     fence_proxy_async();
     mbar_expect_tx(barp, (uint32_t)(t.bw * t.bh * 4));
-    tma_load_3d(tile, &tmap, barp, bx0, by0, (int)blockIdx.z);
+    tma_load_3d(tile, &tmap, barp, ox, oy, (int)blockIdx.z);
   }
   if (threadIdx.x >= 32 && threadIdx.x < 32 + kWarpTH) {
     // row terms, once per tile row: bx = (float)(iM[1]*y + iM[2]) -- f64 mul, f64 add, one rounding
@@ -376,7 +377,9 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
     const float by = __double2float_rn(__dadd_rn(__dmul_rn(a.m4, y), a.m5));
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(rowtab + r * 8), "f"(bx), "f"(by) : "memory");
   }
-  __syncthreads();  // barrier init and row terms visible
+  __syncthreads();  // barrier init, box origin and row terms visible
+  int bx0, by0;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bx0), "=r"(by0) : "r"(barp + 8));
   const int lx = threadIdx.x & 63, ly0 = threadIdx.x >> 6;
   const int x = tx0 + lx;
   const float xf = (float)x;

@@ -33,6 +33,7 @@ struct Gauss5Op {
   static constexpr int P = 2;    // pixels of horizontal halo
   static constexpr int E = CN;   // bytes per pixel
   static constexpr int NOUT = 1;
+  static constexpr int UNROLL = 8;  // rows unrolled in the hot loop (window period 4; 8 measured faster: 8.05 vs 8.55 us)
   uint32_t win[4][8];  // last 4 rows, unpacked: [2w] = bytes 0,2 of word w; [2w+1] = bytes 1,3
 
   __device__ __forceinline__ void init(const StripParams &) {}

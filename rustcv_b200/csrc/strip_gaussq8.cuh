@@ -21,6 +21,7 @@ struct GaussQ8Op {
   static constexpr int E = CN;
   static constexpr int NOUT = 1;
   static constexpr int WIN = KS == 3 ? 2 : KS == 5 ? 4 : 8;  // window slots (power of two >= KS-1)
+  static constexpr int UNROLL = WIN;  // rows unrolled in the hot loop = window period (measured: 3x3 69% vs 64% of roofline at 8)
   static constexpr int EXT = (HV * CN + 3) / 4;              // neighbour words needed on each side
   static_assert(KS == 3 || KS == 5 || KS == 7, "kernel size");
   static_assert(EXT <= 3, "taps beyond three words");

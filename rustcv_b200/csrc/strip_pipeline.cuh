@@ -184,40 +184,50 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       if (fast_strip && c * R + R <= n_feed) {
         // whole chunk of an aligned, non-ragged strip: every row is fed; every row emits except the
         // first 2*HV rows of the band (chunk 0), which only fill the window.  No per-row tests.
-        const uint32_t rowaddr = tile + lane * kLaneBytes;
+        // The body is unrolled Op::UNROLL rows (the op's window period) and looped R/UNROLL times:
+        // unrolling all 8 rows of the wider ops would not fit the 32 KB instruction cache.
+        constexpr int U = Op::UNROLL;
+        static_assert(R % U == 0, "window period must divide the chunk");
+#pragma unroll 1
+        for (int g = 0; g < R / U; ++g) {
+          const uint32_t rowaddr = tile + (uint32_t)(g * U) * kTileBytes + lane * kLaneBytes;
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const uint4 q = lds128(rowaddr + j * kTileBytes);
-          if (j < 2 * HV && c == 0) {
-            if (j == 0) op.template warm<0>(q);
-            if (j == 1) op.template warm<1>(q);
-            if (j == 2) op.template warm<2>(q);
-            if (j == 3) op.template warm<3>(q);
-            if (j == 4) op.template warm<4>(q);
-            if (j == 5) op.template warm<5>(q);
-            continue;
+          for (int j = 0; j < U; ++j) {
+            const uint4 q = lds128(rowaddr + j * kTileBytes);
+            if (c == 0 && g * U + j < 2 * HV) {
+              if (j == 0) op.template warm<0>(q);
+              if (j == 1) op.template warm<1>(q);
+              if (j == 2) op.template warm<2>(q);
+              if (j == 3) op.template warm<3>(q);
+              if (j == 4) op.template warm<4>(q);
+              if (j == 5) op.template warm<5>(q);
+              if (j == 6) op.template warm<6>(q);
+              if (j == 7) op.template warm<7>(q);
+              continue;
+            }
+            if (j == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
+            if (j == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
+            if (j == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
+            if (j == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
+            if (j == 4) op.template feed<4, true>(q, true, optr, nvalid, true);
+            if (j == 5) op.template feed<5, true>(q, true, optr, nvalid, true);
+            if (j == 6) op.template feed<6, true>(q, true, optr, nvalid, true);
+            if (j == 7) op.template feed<7, true>(q, true, optr, nvalid, true);
+#pragma unroll
+            for (int k = 0; k < Op::NOUT; ++k)
+              if (Op::NOUT == 1 || optr[k]) optr[k] += p.out[k].step;
           }
-          if (j == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
-          if (j == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
-          if (j == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
-          if (j == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
-          if (j == 4) op.template feed<4, true>(q, true, optr, nvalid, true);
-          if (j == 5) op.template feed<5, true>(q, true, optr, nvalid, true);
-          if (j == 6) op.template feed<6, true>(q, true, optr, nvalid, true);
-          if (j == 7) op.template feed<7, true>(q, true, optr, nvalid, true);
-#pragma unroll
-          for (int k = 0; k < Op::NOUT; ++k)
-            if (Op::NOUT == 1 || optr[k]) optr[k] += p.out[k].step;
         }
         continue;
       }
       // first / last chunks of a band, ragged or unaligned strips: per-row tests
-      {
-        const uint32_t rowaddr = tile + lane * kLaneBytes;
+#pragma unroll 1
+      for (int g = 0; g < R / Op::UNROLL; ++g) {
+        const uint32_t rowaddr = tile + (uint32_t)(g * Op::UNROLL) * kTileBytes + lane * kLaneBytes;
         // feed index fi produces output row y0 + fi - 2*HV
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int fi = c * R + j;
+        for (int j = 0; j < Op::UNROLL; ++j) {
+          const int fi = c * R + g * Op::UNROLL + j;
           if (fi < n_feed) {
             const uint4 q = lds128(rowaddr + j * kTileBytes);
             const bool emit = fi >= 2 * HV;
