@@ -210,17 +210,15 @@ def bind_to_gpu_numa_node(local: int) -> str:
     try:
         import torch
 
-        bus = torch.cuda.get_device_properties(local).pci_bus_id  # type: ignore[attr-defined]
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
     except Exception:
         try:
-            out = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+            bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
                                           text=True).strip()
-            bus = out
         except Exception as e:  # noqa: BLE001
             return f"unbound ({e})"
     try:
-        if isinstance(bus, int):
-            return "unbound (no bus id string)"
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit domain
             bus = bus[4:]
@@ -267,6 +265,7 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: rustcv_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -394,6 +393,7 @@ def main() -> None:
             "parity": {"device_frame0_crc_827081c8": crc_ok, "e2e_frame0_crc_827081c8": e2e_ok},
         }
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again
             cores = host_cores()
             v_all, s_all = cpu_gaussian_mpix(16 if cores >= 8 else 4, cores)
             v_one, s_one = cpu_gaussian_mpix(4, 1)
