@@ -148,8 +148,17 @@ int launch_sepfilter_q8(Ctx *, const DBatch &src, const DBatch &dst, const int32
   return launch_sep<uint8_t>(src, dst, kx, kw, ky, kh, s);
 }
 
-int launch_sepfilter_f32(Ctx *, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky,
+int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
+                        cudaStream_t s);
+int launch_filter2d_f32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                              cudaStream_t s);
+
+int launch_sepfilter_f32(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky,
                          int kh, cudaStream_t s) {
+  if (opt_get("sepf32.force_generic", 0) == 0 && src.v.rows > 0 && src.v.cols > 0 && src.n > 0) {
+    int rc = launch_sepf32_strip(c, src, dst, kx, kw, ky, kh, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
   return launch_sep<float>(src, dst, kx, kw, ky, kh, s);
 }
 
@@ -318,6 +327,10 @@ int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k
   if (kw < 1 || kh < 1 || kw > kMaxTaps || kh > kMaxTaps)
     return fail(RCV_ERR_ARG, "kernel size %dx%d outside 1..%d", kw, kh, kMaxTaps);
   if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (opt_get("f2d.force_generic", 0) == 0) {
+    int rc = launch_filter2d_f32_strip(c, src, dst, k, kw, kh, delta, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
   void *dtaps = nullptr;
   RCV_TRY(ctx_scratch(c, SCR_TAPS, (size_t)kw * kh * sizeof(float), &dtaps));
   RCV_CUDA(cudaMemcpyAsync(dtaps, k, (size_t)kw * kh * sizeof(float), cudaMemcpyHostToDevice, s));

@@ -1,0 +1,192 @@
+// strip_f32.cu -- f32 single-channel ops of the TMA strip pipeline (see strip_pipeline.cuh):
+//   SepF32Op<KS>     separable KS x KS filter (GaussianBlur / sepFilter2D on gray f32), KS = 3, 5, 7
+//   Filter2dF32Op<KS> dense KS x KS correlation, KS = 3, 5
+// Operation order is the oracle's (orc_sepfilter_f32 / orc_filter2d_f32): fmaf chains in
+// ascending tap order, row pass before column pass -- results are bit-identical.
+#include "strip_pipeline.cuh"
+
+namespace rcv {
+
+template <int KS>
+struct SepF32Op {
+  static constexpr int HV = KS / 2;
+  static constexpr int P = KS / 2;
+  static constexpr int E = 4;
+  static constexpr int NOUT = 1;
+  static constexpr int WIN = KS == 3 ? 2 : KS == 5 ? 4 : 8;
+  static constexpr int UNROLL = WIN;
+  float win[WIN][4];  // row-filtered previous rows
+  float kx[KS], ky[KS];
+
+  __device__ __forceinline__ void init(const StripParams &p) {
+#pragma unroll
+    for (int i = 0; i < KS; ++i) {
+      kx[i] = p.ftaps[i];
+      ky[i] = p.ftaps[KS + i];
+    }
+  }
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int j = 0; j < WIN; ++j)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) win[j][h] = 0.0f;
+  }
+
+  // row pass of one source row: h[c] = fmaf chain over kx, ascending, from 0
+  __device__ __forceinline__ void rowpass(const uint4 &q, float (&h)[4]) const {
+    float x[4 + 2 * P];  // columns -P .. 3+P
+    x[P + 0] = __uint_as_float(q.x);
+    x[P + 1] = __uint_as_float(q.y);
+    x[P + 2] = __uint_as_float(q.z);
+    x[P + 3] = __uint_as_float(q.w);
+#pragma unroll
+    for (int e = 0; e < P; ++e) {
+      x[e] = __shfl_up_sync(0xffffffffu, x[P + 4 - P + e], 1);        // left lane's last P columns
+      x[P + 4 + e] = __shfl_down_sync(0xffffffffu, x[P + e], 1);      // right lane's first P columns
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) acc = fmaf(kx[j], x[c + j], acc);
+      h[c] = acc;
+    }
+  }
+
+  template <int J8>
+  __device__ __forceinline__ void warm(const uint4 &q) {
+    float h[4];
+    rowpass(q, h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) win[J8 & (WIN - 1)][c] = h[c];
+  }
+
+  template <int J8, bool FAST>
+  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
+    float h[4], v[4];
+    rowpass(q, h);  // shuffles: executed by the whole warp whether or not the row emits
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < KS - 1; ++i) acc = fmaf(ky[i], win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][c], acc);
+      v[c] = fmaf(ky[KS - 1], h[c], acc);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) win[J8 & (WIN - 1)][c] = h[c];
+    if (!FAST && !emit) return;
+    float *o = (float *)outp[0];
+    if (FAST) {
+      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid == 16 && vec) {
+      *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 4 < nvalid) o[c] = v[c];
+    }
+  }
+};
+
+// dense KS x KS correlation: acc = delta; acc = fmaf(k[i][j], p[y+i-r][x+j-r], acc), row-major taps
+template <int KS>
+struct Filter2dF32Op {
+  static constexpr int HV = KS / 2;
+  static constexpr int P = KS / 2;
+  static constexpr int E = 4;
+  static constexpr int NOUT = 1;
+  static constexpr int WIN = KS == 3 ? 2 : 4;
+  static constexpr int UNROLL = WIN;
+  static constexpr int XW = 4 + 2 * P;
+  float win[WIN][XW];  // previous source rows, columns -P .. 3+P
+  float k[KS * KS];
+  float delta;
+
+  __device__ __forceinline__ void init(const StripParams &p) {
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) k[i] = p.ftaps[i];
+    delta = p.ftaps[KS * KS];
+  }
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int j = 0; j < WIN; ++j)
+#pragma unroll
+      for (int h = 0; h < XW; ++h) win[j][h] = 0.0f;
+  }
+  __device__ __forceinline__ void widen(const uint4 &q, float (&x)[XW]) const {
+    x[P + 0] = __uint_as_float(q.x);
+    x[P + 1] = __uint_as_float(q.y);
+    x[P + 2] = __uint_as_float(q.z);
+    x[P + 3] = __uint_as_float(q.w);
+#pragma unroll
+    for (int e = 0; e < P; ++e) {
+      x[e] = __shfl_up_sync(0xffffffffu, x[P + 4 - P + e], 1);
+      x[P + 4 + e] = __shfl_down_sync(0xffffffffu, x[P + e], 1);
+    }
+  }
+  template <int J8>
+  __device__ __forceinline__ void warm(const uint4 &q) {
+    float x[XW];
+    widen(q, x);
+#pragma unroll
+    for (int c = 0; c < XW; ++c) win[J8 & (WIN - 1)][c] = x[c];
+  }
+  template <int J8, bool FAST>
+  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
+    float x[XW], v[4];
+    widen(q, x);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = delta;
+#pragma unroll
+      for (int i = 0; i < KS - 1; ++i)
+#pragma unroll
+        for (int j = 0; j < KS; ++j) acc = fmaf(k[i * KS + j], win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][c + j], acc);
+#pragma unroll
+      for (int j = 0; j < KS; ++j) acc = fmaf(k[(KS - 1) * KS + j], x[c + j], acc);
+      v[c] = acc;
+    }
+#pragma unroll
+    for (int c = 0; c < XW; ++c) win[J8 & (WIN - 1)][c] = x[c];
+    if (!FAST && !emit) return;
+    float *o = (float *)outp[0];
+    if (FAST) {
+      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid == 16 && vec) {
+      *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 4 < nvalid) o[c] = v[c];
+    }
+  }
+};
+
+// separable f32, single channel, kw == kh in {3, 5, 7}; RCV_ERR_UNSUPPORTED otherwise
+int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
+                        cudaStream_t s) {
+  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
+  float taps[14];
+  if (kw != 3 && kw != 5 && kw != 7) return RCV_ERR_UNSUPPORTED;
+  for (int i = 0; i < kw; ++i) {
+    taps[i] = kx[i];
+    taps[kw + i] = ky[i];
+  }
+  if (kw == 3) return launch_strip<SepF32Op<3>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 6);
+  if (kw == 5) return launch_strip<SepF32Op<5>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 10);
+  return launch_strip<SepF32Op<7>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 14);
+}
+
+// dense f32, single channel, 3x3 or 5x5
+int launch_filter2d_f32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                              cudaStream_t s) {
+  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
+  if (kw != 3 && kw != 5) return RCV_ERR_UNSUPPORTED;
+  float taps[26];
+  for (int i = 0; i < kw * kh; ++i) taps[i] = k[i];
+  taps[kw * kh] = delta;
+  if (kw == 3) return launch_strip<Filter2dF32Op<3>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, 10);
+  return launch_strip<Filter2dF32Op<5>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, 26);
+}
+
+}  // namespace rcv

@@ -52,6 +52,7 @@ struct StripParams {
   long long total_items;
   unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
   uint32_t taps_x[4], taps_y[4];  // GaussQ8Op: symmetric Q8 taps, [0] outermost .. [KS/2] centre
+  float ftaps[52];                // SepF32Op: kx[0..KS) then ky[0..KS); Filter2dOp: KS*KS taps row-major, then delta
 };
 
 // ---------------------------------------------------------------------------------------
@@ -287,7 +288,8 @@ static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int stri
 
 template <class Op>
 static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout, const char *band_opt,
-                        cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr) {
+                        cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr,
+                        const float *ftaps = nullptr, int nftaps = 0) {
   CUtensorMap tmap;
   RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
                              kTileBytes / 4, kR));
@@ -313,6 +315,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     p.taps_x[i] = taps_x ? (uint32_t)taps_x[i] : 0;
     p.taps_y[i] = taps_y ? (uint32_t)taps_y[i] : 0;
   }
+  for (int i = 0; i < 52; ++i) p.ftaps[i] = (ftaps && i < nftaps) ? ftaps[i] : 0.0f;
 
   auto kern = k_strip<Op, kR, kS, kNW>;
   const int smem = kNW * kS * kR * kTileBytes + kNW * kS * 8;

@@ -355,6 +355,37 @@ def test_sep_filter2d(rcv, oracle):
     assert_same(d.to_numpy(), oracle.sepfilter_u8_q8(u, qx, qy), "sepfilter q8")
 
 
+@pytest.mark.parametrize("ks", [3, 5, 7])
+def test_f32_strip_kernels(rcv, oracle, ks):
+    """k_strip<SepF32Op<KS>> / k_strip<Filter2dF32Op<KS>>: gray f32, multi-strip, ragged edge, seams."""
+    R = rcv
+    rng = np.random.default_rng(ks)
+    h, w = 203, 517
+    a = oracle.fill_f32(150 + ks, h * w).reshape(h, w)
+    s = mats(R, a, "device")
+    d = s.like()
+    kx = rng.normal(size=ks).astype(np.float32)
+    ky = rng.normal(size=ks).astype(np.float32)
+    R.imgproc.sep_filter2d(s, d, kx, ky)
+    assert_f32(d.to_numpy(), oracle.sepfilter_f32(a, kx, ky), f"sepf32 strip ks{ks}", max_ulp=0)
+    R.imgproc.gaussian_blur(s, d, (ks, ks), 1.3)
+    assert_f32(d.to_numpy(), oracle.gaussian_blur(a, (ks, ks), 1.3, 1.3), f"gauss f32 strip ks{ks}", max_ulp=0)
+    if ks <= 5:
+        k = rng.normal(size=(ks, ks)).astype(np.float32)
+        R.imgproc.filter2d(s, d, k, delta=-0.5)
+        assert_f32(d.to_numpy(), oracle.filter2d(a, k, -0.5), f"filter2d f32 strip ks{ks}", max_ulp=0)
+    # the generic kernels agree
+    R.imgproc.set_option("sepf32.force_generic", 1)
+    R.imgproc.set_option("f2d.force_generic", 1)
+    try:
+        d2 = s.like()
+        R.imgproc.sep_filter2d(s, d2, kx, ky)
+        assert_f32(d2.to_numpy(), oracle.sepfilter_f32(a, kx, ky), f"sepf32 generic ks{ks}", max_ulp=0)
+    finally:
+        R.imgproc.set_option("sepf32.force_generic", 0)
+        R.imgproc.set_option("f2d.force_generic", 0)
+
+
 @pytest.mark.parametrize("ksz", [(3, 3), (5, 5), (7, 3), (4, 4), (1, 1), (9, 9)])
 def test_filter2d(rcv, oracle, ksz):
     R = rcv
