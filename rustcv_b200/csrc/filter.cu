@@ -152,6 +152,8 @@ int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const floa
                         cudaStream_t s);
 int launch_filter2d_f32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
                               cudaStream_t s);
+int launch_filter2d_u8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                             cudaStream_t s);
 
 int launch_sepfilter_f32(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky,
                          int kh, cudaStream_t s) {
@@ -328,7 +330,8 @@ int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k
     return fail(RCV_ERR_ARG, "kernel size %dx%d outside 1..%d", kw, kh, kMaxTaps);
   if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
   if (opt_get("f2d.force_generic", 0) == 0) {
-    int rc = launch_filter2d_f32_strip(c, src, dst, k, kw, kh, delta, s);
+    int rc = src.v.depth == RCV_F32 ? launch_filter2d_f32_strip(c, src, dst, k, kw, kh, delta, s)
+                                    : launch_filter2d_u8_strip(c, src, dst, k, kw, kh, delta, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
   void *dtaps = nullptr;

@@ -386,6 +386,25 @@ def test_f32_strip_kernels(rcv, oracle, ks):
         R.imgproc.set_option("f2d.force_generic", 0)
 
 
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+def test_filter2d_u8_3x3_strip_kernel(rcv, oracle, cn):
+    """k_strip<Filter2dU8Op<CN>>: sharpen / Laplacian / random taps incl. exact .5 ties and saturation."""
+    R = rcv
+    rng = np.random.default_rng(cn)
+    h, w = 203, 517
+    a = oracle.fill_u8(160 + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+    s = mats(R, a, "device")
+    d = s.like()
+    kernels = [np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32),           # sharpen (saturates both ways)
+               np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32),               # Laplacian
+               np.full((3, 3), 0.125, np.float32),                                     # exact binary fractions: .5 ties
+               rng.normal(size=(3, 3)).astype(np.float32) / 3]
+    for i, k in enumerate(kernels):
+        for delta in (0.0, 0.5):
+            R.imgproc.filter2d(s, d, k, delta=delta)
+            assert_same(d.to_numpy(), oracle.filter2d(a, k, delta), f"filter2d u8 3x3 cn{cn} kernel{i} delta{delta}")
+
+
 @pytest.mark.parametrize("ksz", [(3, 3), (5, 5), (7, 3), (4, 4), (1, 1), (9, 9)])
 def test_filter2d(rcv, oracle, ksz):
     R = rcv
