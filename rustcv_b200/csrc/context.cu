@@ -90,6 +90,7 @@ int ctx_scratch(Ctx *c, int slot, size_t bytes, void **ptr) {
     size_t want = bytes + bytes / 8 + 256;
     RCV_CUDA(cudaMalloc(&c->scratch[slot], want));
     c->scratch_bytes[slot] = want;
+    if (slot == SCR_TABLE_X || slot == SCR_TABLE_Y) memset(c->resize_key, 0, sizeof(c->resize_key));
   }
   *ptr = c->scratch[slot];
   return RCV_OK;

@@ -12,6 +12,7 @@
 #include "tma_ptx.cuh"
 
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace rcv {
@@ -169,17 +170,21 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
     RCV_CUDA(cudaGetLastError());
     return RCV_OK;
   }
-  std::vector<ResizeCol> cols;
-  std::vector<ResizeRow> rows;
-  resize_tables(src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, cols, rows);
+  // the per-column / per-row tables depend on the geometry only: rebuilt and uploaded when it changes
   void *dcols = nullptr, *drows = nullptr;
-  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, cols.size() * sizeof(ResizeCol), &dcols));
-  RCV_TRY(ctx_scratch(c, SCR_TABLE_Y, rows.size() * sizeof(ResizeRow), &drows));
-  RCV_CUDA(cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(ResizeCol), cudaMemcpyHostToDevice, s));
-  RCV_CUDA(cudaMemcpyAsync(drows, rows.data(), rows.size() * sizeof(ResizeRow), cudaMemcpyHostToDevice, s));
-  // the vectors die at return: pageable-source async copies are staged before returning,
-  // but make that independent of driver behaviour
-  RCV_CUDA(cudaStreamSynchronize(s));
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, (size_t)dst.v.cols * sizeof(ResizeCol), &dcols));
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_Y, (size_t)dst.v.rows * sizeof(ResizeRow), &drows));
+  const int key[4] = {src.v.rows, src.v.cols, dst.v.rows, dst.v.cols};
+  if (memcmp(key, c->resize_key, sizeof(key)) != 0) {
+    std::vector<ResizeCol> cols;
+    std::vector<ResizeRow> rows;
+    resize_tables(src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, cols, rows);
+    RCV_CUDA(cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(ResizeCol), cudaMemcpyHostToDevice, s));
+    RCV_CUDA(cudaMemcpyAsync(drows, rows.data(), rows.size() * sizeof(ResizeRow), cudaMemcpyHostToDevice, s));
+    // the vectors die at return: do not depend on how the driver stages pageable sources
+    RCV_CUDA(cudaStreamSynchronize(s));
+    memcpy(c->resize_key, key, sizeof(key));
+  }
   a.cols = (const ResizeCol *)dcols;
   a.rows = (const ResizeRow *)drows;
   dim3 grid(ceil_div(dst.v.cols, 256), dst.v.rows, src.n);
