@@ -290,59 +290,85 @@ constexpr int kWarpTW = 64, kWarpTH = 32, kWarpThreads = 256;
 struct WarpTileArgs {
   WarpArgs a;
   double d0, d3;  // iM[0], iM[3] in f64 for the tile's bounding box
-  int bw, bh;     // box size in pixels
+  int bw, bh;     // box size: bw 4-byte words per row, bh rows
 };
 
-// One pixel.  INTERIOR: the whole box lies inside the image, so every tap is in-image and
-// inside the box -- no predicates at all.  Same operations in the same order either way.
-template <bool INTERIOR>
-__device__ __forceinline__ float warp_pixel(const WarpTileArgs &t, uint32_t tile, int bx0, int by0, float sx, float sy,
-                                            const uint8_t *src) {
+// One pixel (all CN channels).  INTERIOR: the whole box lies inside the image, so every tap is
+// in-image and inside the box -- no predicates at all.  Same operations in the same order either
+// way.  T = float (CN == 1) or uint8_t (CN = 1..4); box geometry is in BYTES (bx0 is a byte offset).
+template <typename T, int CN>
+__device__ __forceinline__ float tap_load(uint32_t addr) {
+  if (sizeof(T) == 4) return lds_f32(addr);
+  return (float)lds8(addr);
+}
+
+template <typename T, int CN, bool INTERIOR>
+__device__ __forceinline__ void warp_pixel(const WarpTileArgs &t, uint32_t tile, int bx0, int by0, float sx, float sy,
+                                           const uint8_t *src, T *out) {
+  constexpr int E = CN * (int)sizeof(T);  // bytes per pixel
   const WarpArgs &a = t.a;
   const float flx = floorf(sx), fly = floorf(sy);
   const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
-  float p00, p01, p10, p11;
-  if (INTERIOR) {
-    const int cx = (int)flx - bx0, cy = (int)fly - by0;
-    const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
-    p00 = lds_f32(p);
-    p01 = lds_f32(p + 4);
-    p10 = lds_f32(p + t.bw * 4);
-    p11 = lds_f32(p + t.bw * 4 + 4);
-  } else {
-    const bool inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
-    const int ix = inside ? (int)flx : 0, iy = inside ? (int)fly : 0;
-    const bool x0ok = inside && ix >= 0, x1ok = inside && ix + 1 < a.scols;
-    const bool y0ok = inside && iy >= 0, y1ok = inside && iy + 1 < a.srows;
-    const int cx = ix - bx0, cy = iy - by0;  // tap (0,0) inside the box
-    const bool inbox = (unsigned)cx < (unsigned)(t.bw - 1) && (unsigned)cy < (unsigned)(t.bh - 1);
-    p00 = p01 = p10 = p11 = a.border;
-    if (inbox) {
-      const uint32_t p = tile + (uint32_t)(cy * t.bw + cx) * 4;
-      const float v00 = lds_f32(p), v01 = lds_f32(p + 4), v10 = lds_f32(p + t.bw * 4), v11 = lds_f32(p + t.bw * 4 + 4);
-      if (y0ok && x0ok) p00 = v00;
-      if (y0ok && x1ok) p01 = v01;
-      if (y1ok && x0ok) p10 = v10;
-      if (y1ok && x1ok) p11 = v11;
-    } else if (inside) {  // cannot happen for sane boxes; keeps the result exact regardless
-      const float *r0 = (const float *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
-      const float *r1 = (const float *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
-      if (y0ok && x0ok) p00 = __ldg(r0 + ix);
-      if (y0ok && x1ok) p01 = __ldg(r0 + ix + 1);
-      if (y1ok && x0ok) p10 = __ldg(r1 + ix);
-      if (y1ok && x1ok) p11 = __ldg(r1 + ix + 1);
+  const int rowb = t.bw * 4;  // box row pitch in bytes
+  bool inside = true, x0ok = true, x1ok = true, y0ok = true, y1ok = true, inbox = true;
+  int ix = (int)flx, iy = (int)fly;
+  if (!INTERIOR) {
+    inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
+    ix = inside ? ix : 0;
+    iy = inside ? iy : 0;
+    x0ok = inside && ix >= 0;
+    x1ok = inside && ix + 1 < a.scols;
+    y0ok = inside && iy >= 0;
+    y1ok = inside && iy + 1 < a.srows;
+  }
+  const int cxb = ix * E - bx0, cy = iy - by0;  // byte offset of tap (0,0) inside the box
+  if (!INTERIOR) inbox = cxb >= 0 && cxb + 2 * E <= rowb && (unsigned)cy < (unsigned)(t.bh - 1);
+  const uint32_t p = tile + (uint32_t)(cy * rowb + cxb);
+#pragma unroll
+  for (int ch = 0; ch < CN; ++ch) {
+    float p00, p01, p10, p11;
+    if (INTERIOR) {
+      p00 = tap_load<T, CN>(p + ch * sizeof(T));
+      p01 = tap_load<T, CN>(p + E + ch * sizeof(T));
+      p10 = tap_load<T, CN>(p + rowb + ch * sizeof(T));
+      p11 = tap_load<T, CN>(p + rowb + E + ch * sizeof(T));
+    } else {
+      p00 = p01 = p10 = p11 = a.border;
+      if (inbox) {
+        const float v00 = tap_load<T, CN>(p + ch * sizeof(T)), v01 = tap_load<T, CN>(p + E + ch * sizeof(T));
+        const float v10 = tap_load<T, CN>(p + rowb + ch * sizeof(T)), v11 = tap_load<T, CN>(p + rowb + E + ch * sizeof(T));
+        if (y0ok && x0ok) p00 = v00;
+        if (y0ok && x1ok) p01 = v01;
+        if (y1ok && x0ok) p10 = v10;
+        if (y1ok && x1ok) p11 = v11;
+      } else if (inside) {  // cannot happen for sane boxes; keeps the result exact regardless
+        const T *r0 = (const T *)(src + (size_t)(y0ok ? iy : 0) * a.sstep);
+        const T *r1 = (const T *)(src + (size_t)(y1ok ? iy + 1 : 0) * a.sstep);
+        if (y0ok && x0ok) p00 = (float)__ldg(r0 + ix * CN + ch);
+        if (y0ok && x1ok) p01 = (float)__ldg(r0 + (ix + 1) * CN + ch);
+        if (y1ok && x0ok) p10 = (float)__ldg(r1 + ix * CN + ch);
+        if (y1ok && x1ok) p11 = (float)__ldg(r1 + (ix + 1) * CN + ch);
+      }
+    }
+    const float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
+    const float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
+    const float v = fmaf(fy, __fsub_rn(q1, q0), q0);
+    if (sizeof(T) == 1) {
+      const int iv = __float2int_rn(v);
+      out[ch] = (T)min(max(iv, 0), 255);
+    } else {
+      out[ch] = (T)v;
     }
   }
-  const float q0 = fmaf(fx, __fsub_rn(p01, p00), p00);
-  const float q1 = fmaf(fx, __fsub_rn(p11, p10), p10);
-  return fmaf(fy, __fsub_rn(q1, q0), q0);
 }
 
-__global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_constant__ CUtensorMap tmap,
-                                                                const WarpTileArgs t) {
+template <typename T, int CN>
+__global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constant__ CUtensorMap tmap,
+                                                            const WarpTileArgs t) {
   // no static shared memory in this kernel: the TMA destination must be 128-byte aligned and the
   // dynamic segment only starts at offset 0 when nothing static precedes it.  Layout:
-  // [tile bw*bh floats][mbarrier, 16 B][row terms: TH x (bx, by) floats]
+  // [tile bw words x bh rows][mbarrier 8 B, box origin 8 B][row terms: TH x (bx, by) floats]
+  constexpr int E = CN * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const WarpArgs &a = t.a;
   const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * kWarpTH;
@@ -365,14 +391,14 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
     // clamp far-out-of-image boxes so the int conversion and the TMA coordinates stay sane
     minx = fmin(fmax(minx, -1.0e6), 1.0e6 + a.scols);
     miny = fmin(fmax(miny, -1.0e6), 1.0e6 + a.srows);
-    // the box starts on a 16-byte boundary of the row (4 floats): TMA rejects other inner offsets
-    const int ox = ((int)floor(minx) - 1) & ~3, oy = (int)floor(miny) - 1;
+    // the box starts on a 16-byte boundary of the row: TMA rejects other inner offsets
+    const int ox = (((int)floor(minx) - 1) * E) & ~15, oy = (int)floor(miny) - 1;  // ox in bytes
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(barp + 8), "r"(ox), "r"(oy) : "memory");
     mbar_init(barp, 1);
     fence_mbar_init();
     fence_proxy_async();
     mbar_expect_tx(barp, (uint32_t)(t.bw * t.bh * 4));
-    tma_load_3d(tile, &tmap, barp, ox, oy, (int)blockIdx.z);
+    tma_load_3d(tile, &tmap, barp, ox >> 2, oy, (int)blockIdx.z);
   }
   if (threadIdx.x >= 32 && threadIdx.x < 32 + kWarpTH) {
     // row terms, once per tile row: bx = (float)(iM[1]*y + iM[2]) -- f64 mul, f64 add, one rounding
@@ -389,8 +415,8 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
   const int x = tx0 + lx;
   const float xf = (float)x;
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
-  float *drow = (float *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)(ty0 + ly0) * a.dstep) + x;
-  const bool interior = bx0 >= 0 && by0 >= 0 && bx0 + t.bw <= a.scols && by0 + t.bh <= a.srows;
+  uint8_t *drow = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)(ty0 + ly0) * a.dstep + (size_t)x * E;
+  const bool interior = bx0 >= 0 && by0 >= 0 && bx0 + t.bw * 4 <= a.scols * E && by0 + t.bh <= a.srows;
   const bool full = tx0 + kWarpTW <= a.dcols && ty0 + kWarpTH <= a.drows;
   mbar_wait(barp, 0);
   if (interior && full) {
@@ -398,8 +424,11 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
     for (int k = 0; k < kWarpTH / 4; ++k) {
       float bx, by;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
-      const float v = warp_pixel<true>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src);
-      *(float *)((uint8_t *)drow + (size_t)(4 * k) * a.dstep) = v;
+      T v[CN];
+      warp_pixel<T, CN, true>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src, v);
+      T *o = (T *)(drow + (size_t)(4 * k) * a.dstep);
+#pragma unroll
+      for (int ch = 0; ch < CN; ++ch) o[ch] = v[ch];
     }
   } else {
 #pragma unroll 2
@@ -407,10 +436,24 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_f32_tile(const __grid_con
       const int y = ty0 + ly0 + 4 * k;
       float bx, by;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
-      const float v = warp_pixel<false>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src);
-      if (x < a.dcols && y < a.drows) *(float *)((uint8_t *)drow + (size_t)(4 * k) * a.dstep) = v;
+      T v[CN];
+      warp_pixel<T, CN, false>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src, v);
+      if (x < a.dcols && y < a.drows) {
+        T *o = (T *)(drow + (size_t)(4 * k) * a.dstep);
+#pragma unroll
+        for (int ch = 0; ch < CN; ++ch) o[ch] = v[ch];
+      }
     }
   }
+}
+
+template <typename T, int CN>
+static int launch_warp_tile(const CUtensorMap &tmap, const WarpTileArgs &t, dim3 grid, size_t smem, cudaStream_t s) {
+  RCV_CUDA(cudaFuncSetAttribute(k_warp_tile<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_warp_tile<T, CN><<<grid, kWarpThreads, smem, s>>>(tmap, t);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
 }
 
 int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const double iM[6], double border,
@@ -437,9 +480,11 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
   a.m5 = iM[5];
   a.border = src.v.depth == RCV_U8 ? (float)(int)border : (float)border;
 
-  // TMA-staged path: f32 C1, 16-byte aligned source, bounding box small enough for shared memory
-  if (src.v.depth == RCV_F32 && src.v.cn == 1 && src.v.rows > 0 && src.v.cols > 0 &&
+  // TMA-staged path: f32 C1 or u8 C1..C4, 16-byte aligned source, bounding box small enough for smem
+  const bool tile_type = (src.v.depth == RCV_F32 && src.v.cn == 1) || src.v.depth == RCV_U8;
+  if (tile_type && src.v.rows > 0 && src.v.cols > 0 &&
       ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 15) == 0) && opt_get("warp.force_generic", 0) == 0) {
+    const int E = (int)src.v.elem() * src.v.cn;  // bytes per pixel
     const double dxw = fabs(iM[0]) * (kWarpTW - 1) + fabs(iM[1]) * (kWarpTH - 1);
     const double dyh = fabs(iM[3]) * (kWarpTW - 1) + fabs(iM[4]) * (kWarpTH - 1);
     if (dxw < 250.0 && dyh < 250.0) {
@@ -447,9 +492,9 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
       t.a = a;
       t.d0 = iM[0];
       t.d3 = iM[3];
-      // +3: the box origin is floored to a multiple of 4 pixels.  Width = 16 (mod 32) floats keeps the
-      // rotated gather (a lane step of ~(cos, -sin) pixels) spread over the shared-memory banks.
-      t.bw = ((int)ceil(dxw) + 4 + 3 + 15) & ~15;
+      // box width in 4-byte words: (ceil(dxw) + 4) pixels, + 15 bytes because the origin is floored to a
+      // 16-byte boundary.  16 (mod 32) words keeps the rotated gather spread over the smem banks.
+      t.bw = ((((int)ceil(dxw) + 4) * E + 15 + 3) / 4 + 15) & ~15;
       if ((t.bw & 31) == 0) t.bw += 16;
       t.bh = (int)ceil(dyh) + 4;
       const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16 + kWarpTH * 8;  // tile + mbarrier + row terms
@@ -458,11 +503,13 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
         CUtensorMap tmap;
         RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n,
                                    src.frame_stride, t.bw, t.bh));
-        RCV_CUDA(cudaFuncSetAttribute(k_warp_f32_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_warp_f32_tile<<<grid, kWarpThreads, smem, s>>>(tmap, t);
-        count_launch();
-        RCV_CUDA(cudaGetLastError());
-        return RCV_OK;
+        if (src.v.depth == RCV_F32) return launch_warp_tile<float, 1>(tmap, t, grid, smem, s);
+        switch (src.v.cn) {
+          case 1: return launch_warp_tile<uint8_t, 1>(tmap, t, grid, smem, s);
+          case 2: return launch_warp_tile<uint8_t, 2>(tmap, t, grid, smem, s);
+          case 3: return launch_warp_tile<uint8_t, 3>(tmap, t, grid, smem, s);
+          case 4: return launch_warp_tile<uint8_t, 4>(tmap, t, grid, smem, s);
+        }
       }
     }
   }

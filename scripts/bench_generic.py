@@ -79,5 +79,8 @@ if case("resize"):
     report("resize u8c3 4K->1080p (2x, general)", timeit(lambda: I.resize(bgr, d2)), 15 * 1080 * 1920)
     d3 = bgr.like(rows=4320, cols=7680)
     report("resize u8c3 4K->8K (upscale)", timeit(lambda: I.resize(bgr, d3)), (3 * H * W + 3 * 4320 * 7680))
+if case("warp"):
+    M = I.get_rotation_matrix_2d(((W - 1) / 2, (H - 1) / 2), 15.0)
+    report("warpAffine u8c3 4K 15deg", timeit(lambda: I.warp_affine(bgr, out3, M)), 6 * H * W)
 if case("single"):
     report("gauss5 single 4K frame (1 launch)", timeit(lambda: I.gaussian_blur(bgr, out3, (5, 5), 0.0), steps=50), 6 * H * W)

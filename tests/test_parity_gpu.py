@@ -527,6 +527,27 @@ def test_warp_affine_f32(rcv, oracle, where, shape, angle, scale):
     assert_f32(d.to_numpy(), oracle.warp_affine(a, M.ravel(), border_value=0.25), f"warp {shape} {angle} {where}", max_ulp=1)
 
 
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("angle,scale", [(15.0, 1.0), (-63.0, 0.8), (90.0, 1.0), (5.0, 2.5)])
+def test_warp_affine_u8_tile_kernel(rcv, oracle, cn, angle, scale):
+    """k_warp_tile<uint8_t, CN>: TMA-staged boxes in byte geometry, interior and border tiles."""
+    R = rcv
+    h, w = 150, 333
+    a = oracle.fill_u8(190 + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+    M = R.imgproc.get_rotation_matrix_2d(((w - 1) / 2, (h - 1) / 2), angle, scale)
+    s = mats(R, a, "device")
+    d = s.like()
+    R.imgproc.warp_affine(s, d, M, border_value=9)
+    assert_same(d.to_numpy(), oracle.warp_affine(a, M.ravel(), border_value=9), f"warp u8 cn{cn} {angle} {scale}")
+    R.imgproc.set_option("warp.force_generic", 1)
+    try:
+        d2 = s.like()
+        R.imgproc.warp_affine(s, d2, M, border_value=9)
+        assert_same(d2.to_numpy(), d.to_numpy(), "tile kernel vs direct gather kernel")
+    finally:
+        R.imgproc.set_option("warp.force_generic", 0)
+
+
 def test_warp_affine_u8_and_inverse_map(rcv, oracle):
     R = rcv
     a = oracle.fill_u8(71, 61 * 83 * 3).reshape(61, 83, 3)
@@ -681,3 +702,99 @@ def test_cfg5_warp_full_size_properties(rcv, oracle):
     I = np.array([[1.0, 0, 0], [0, 1.0, 0]])
     R.imgproc.warp_affine(s, d, I)
     assert (d.to_numpy() == a).all()
+
+
+# ---- API contract on the GPU -----------------------------------------------------------------------------
+def test_mixed_locations_and_nonuniform_batches(rcv, oracle):
+    """host src -> device dst, device src -> host dst, and device batches made of separate allocations."""
+    R = rcv
+    a = oracle.fill_u8(170, 90 * 200 * 3).reshape(90, 200, 3)
+    want = oracle.gaussian_blur(a, (5, 5))
+    h = R.Mat.from_numpy(a)
+    d = R.Mat.device_new(90, 200, 3)
+    R.imgproc.gaussian_blur(h, d, (5, 5), 0.0)
+    assert_same(d.to_numpy(), want, "host -> device")
+    back = R.Mat.empty()
+    R.imgproc.gaussian_blur(h.upload(), back, (5, 5), 0.0)
+    assert_same(back.to_numpy(), want, "device -> host")
+    srcs, pads = [], []
+    for j in range(3):  # three separate allocations with odd-sized allocations in between
+        srcs.append(R.Mat.from_numpy(np.roll(a, j, axis=0)).upload())
+        pads.append(R.Mat.device_new(7 + 13 * j, 100, 1))
+    dsts = [s.like() for s in srcs]
+    before = R.imgproc.launch_count()
+    R.imgproc.gaussian_blur_batch(srcs, dsts)
+    # one launch per frame unless the allocator happened to space the frames uniformly
+    assert R.imgproc.launch_count() - before in (1, 3)
+    for j in range(3):
+        assert_same(dsts[j].to_numpy(), oracle.gaussian_blur(np.roll(a, j, axis=0), (5, 5)), f"non-uniform batch {j}")
+
+
+def test_nonblocking_mode_and_sync(rcv, oracle):
+    R = rcv
+    a = oracle.fill_u8(171, 300 * 400 * 3).reshape(300, 400, 3)
+    s = R.Mat.from_numpy(a).upload()
+    d = s.like()
+    R.imgproc.set_blocking(False)
+    try:
+        for _ in range(5):
+            R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)  # enqueue only
+        R.imgproc.sync()
+    finally:
+        R.imgproc.set_blocking(True)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), "non-blocking")
+
+
+def test_concurrent_callers(rcv, oracle):
+    """The ABI is thread-safe for distinct Mats (the reference API is used from one thread per capture)."""
+    import threading
+
+    R = rcv
+    imgs = [oracle.fill_u8(180 + t, 240 * 320 * 3).reshape(240, 320, 3) for t in range(4)]
+    outs = [None] * 4
+    errs = []
+
+    def work(t):
+        try:
+            for _ in range(10):
+                d = R.Mat.empty()
+                R.imgproc.gaussian_blur(R.Mat.from_numpy(imgs[t]), d, (5, 5), 0.0)
+                g = R.Mat.empty()
+                R.imgproc.cvt_color(d, g, R.imgproc.COLOR_BGR2GRAY)
+                outs[t] = (d.to_numpy(), g.to_numpy())
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t in range(4):
+        want = oracle.gaussian_blur(imgs[t], (5, 5))
+        assert_same(outs[t][0], want, f"thread {t} blur")
+        assert_same(outs[t][1], oracle.bgr_to_gray(want), f"thread {t} gray")
+
+
+def test_errors_on_gpu(rcv):
+    R = rcv
+    from rustcv_b200 import _ffi as F
+
+    s = R.Mat.device_new(16, 16, 3)
+    small = R.Mat.device_new(8, 16, 3)
+    with pytest.raises(F.RcvError) as e:
+        R.imgproc.gaussian_blur(s, small, (5, 5), 0.0)  # device dst is never resized by the wrapper
+    assert e.value.code == F.RCV_ERR_SIZE
+    with pytest.raises(F.RcvError) as e:
+        R.imgproc.gaussian_blur(s, s.like(), (4, 4), 0.0)  # even kernel size
+    assert e.value.code == F.RCV_ERR_ARG
+    with pytest.raises(F.RcvError) as e:
+        R.imgproc.gaussian_blur(s, s.like(), (33, 33), 0.0)
+    assert e.value.code == F.RCV_ERR_ARG
+    fake = s.c()
+    fake.device = 7  # not initialised
+    assert F.lib.rcv_gaussian_blur(C.byref(fake), C.byref(s.like().c()), 5, 5, 0.0, 0.0) in (F.RCV_ERR_NOT_INIT, F.RCV_ERR_ARG)
+    # the library is still healthy afterwards
+    d = s.like()
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
