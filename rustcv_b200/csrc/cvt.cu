@@ -45,15 +45,26 @@ struct CvtArgs {
   uint8_t *dst;
   size_t dstep, dfs;
   int rows, cols;
+  int per_row;  // work items (threads) per row
 };
+
+// Threads are numbered over (row, item) so narrow images still fill whole CTAs
+// (a 640-wide YUYV row is only 40 vector items); frames of a batch are blockIdx.y.
+__device__ __forceinline__ bool cvt_index(const CvtArgs &a, int &r, int &i) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.rows * a.per_row) return false;
+  r = (int)(t / a.per_row);
+  i = (int)(t - (long long)r * a.per_row);
+  return true;
+}
 
 // ---- scalar kernels: one thread per pixel / macro-pixel ------------------------------
 template <int CODE>
 __global__ void __launch_bounds__(256) k_cvt_scalar(CvtArgs a) {
-  int r = blockIdx.y;
-  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
-  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int r, i;
+  if (!cvt_index(a, r, i)) return;
+  const uint8_t *s = a.src + (size_t)blockIdx.y * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.y * a.dfs + (size_t)r * a.dstep;
   if (CODE == RCV_COLOR_YUYV2BGR || CODE == RCV_COLOR_UYVY2BGR || CODE == RCV_COLOR_YUYV2GRAY) {
     if (i >= a.cols / 2) return;
     int q0 = s[i * 4], q1 = s[i * 4 + 1], q2 = s[i * 4 + 2], q3 = s[i * 4 + 3];
@@ -131,10 +142,10 @@ __device__ __forceinline__ uint32_t pair16(uint32_t a, uint32_t b) { return __by
 // -> GRAY: 16 px -> 16 B out.
 template <int CODE>
 __global__ void __launch_bounds__(128) k_yuv422_vec(CvtArgs a) {
-  int r = blockIdx.y;
-  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
-  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int r, g;
+  if (!cvt_index(a, r, g)) return;
+  const uint8_t *s = a.src + (size_t)blockIdx.y * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.y * a.dfs + (size_t)r * a.dstep;
   int pairs = a.cols / 2;
   if (g * 8 >= pairs) return;
   if (g * 8 + 8 <= pairs) {
@@ -201,10 +212,10 @@ __global__ void __launch_bounds__(128) k_px16_vec(CvtArgs a) {
                         : (CODE == RCV_COLOR_BGR2GRAY)                            ? 16
                                                                                   : 64;
   constexpr int IN_PX = IN_B / 16, OUT_PX = OUT_B / 16;  // bytes per pixel
-  int r = blockIdx.y;
-  const uint8_t *s = a.src + (size_t)blockIdx.z * a.sfs + (size_t)r * a.sstep;
-  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)r * a.dstep;
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int r, g;
+  if (!cvt_index(a, r, g)) return;
+  const uint8_t *s = a.src + (size_t)blockIdx.y * a.sfs + (size_t)r * a.sstep;
+  uint8_t *d = a.dst + (size_t)blockIdx.y * a.dfs + (size_t)r * a.dstep;
   if (g * 16 >= a.cols) return;
   if (g * 16 + 16 <= a.cols) {
     uint32_t in[IN_B / 4], out[OUT_B / 4];
@@ -309,25 +320,26 @@ static bool aligned16(const DBatch &b) {
 
 template <int CODE>
 static int launch_code(const DBatch &src, const DBatch &dst, cudaStream_t s) {
-  CvtArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows, src.v.cols};
+  CvtArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows, src.v.cols, 0};
   bool vec = aligned16(src) && aligned16(dst);
   constexpr bool yuv = (CODE == RCV_COLOR_YUYV2BGR || CODE == RCV_COLOR_UYVY2BGR || CODE == RCV_COLOR_YUYV2GRAY);
+  const int threads = vec ? 128 : 256;
+  if (vec)
+    a.per_row = yuv ? ceil_div(src.v.cols / 2, 8) : ceil_div(src.v.cols, 16);
+  else
+    a.per_row = yuv ? src.v.cols / 2 : src.v.cols;
+  if (a.per_row == 0) return RCV_OK;
+  const long long total = (long long)a.rows * a.per_row;
+  const long long blocks = (total + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return fail(RCV_ERR_UNSUPPORTED, "image too large");
+  dim3 grid((unsigned)blocks, src.n, 1);
   if (vec) {
-    if constexpr (yuv) {
-      int groups = ceil_div(src.v.cols / 2, 8);
-      if (groups == 0) return RCV_OK;
-      dim3 grid(ceil_div(groups, 128), src.v.rows, src.n);
-      k_yuv422_vec<CODE><<<grid, 128, 0, s>>>(a);
-    } else {
-      int groups = ceil_div(src.v.cols, 16);
-      dim3 grid(ceil_div(groups, 128), src.v.rows, src.n);
-      k_px16_vec<CODE><<<grid, 128, 0, s>>>(a);
-    }
+    if constexpr (yuv)
+      k_yuv422_vec<CODE><<<grid, threads, 0, s>>>(a);
+    else
+      k_px16_vec<CODE><<<grid, threads, 0, s>>>(a);
   } else {
-    int items = yuv ? src.v.cols / 2 : src.v.cols;
-    if (items == 0) return RCV_OK;
-    dim3 grid(ceil_div(items, 256), src.v.rows, src.n);
-    k_cvt_scalar<CODE><<<grid, 256, 0, s>>>(a);
+    k_cvt_scalar<CODE><<<grid, threads, 0, s>>>(a);
   }
   count_launch();
   RCV_CUDA(cudaGetLastError());
@@ -335,7 +347,7 @@ static int launch_code(const DBatch &src, const DBatch &dst, cudaStream_t s) {
 }
 
 int launch_cvt(Ctx *, const DBatch &src, const DBatch &dst, int code, cudaStream_t s) {
-  if (src.v.rows > 65535 || src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "rows/frames > 65535");
+  if (src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "frames > 65535");
   if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
   switch (code) {
     case RCV_COLOR_YUYV2BGR: return launch_code<RCV_COLOR_YUYV2BGR>(src, dst, s);
