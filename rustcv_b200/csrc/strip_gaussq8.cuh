@@ -21,7 +21,11 @@ struct GaussQ8Op {
   static constexpr int E = CN;
   static constexpr int NOUT = 1;
   static constexpr int WIN = KS == 3 ? 2 : KS == 5 ? 4 : 8;  // window slots (power of two >= KS-1)
-  static constexpr int UNROLL = WIN;  // rows unrolled in the hot loop = window period (measured: 3x3 69% vs 64% of roofline at 8)
+  // Rows unrolled in the hot loop = window period (measured: 3x3 69% vs 64% of the roofline at 8).
+  // 7x7: an 8-row unroll is a 42 KB loop (> 32 KB I-cache: 44% of stalls were instruction fetch), so
+  // its window is shifted physically instead (6 rows x 8 register moves per row) and the loop is 1 row.
+  static constexpr bool SHIFT = (KS == 7);
+  static constexpr int UNROLL = SHIFT ? 1 : WIN;
   static constexpr int EXT = (HV * CN + 3) / 4;              // neighbour words needed on each side
   static_assert(KS == 3 || KS == 5 || KS == 7, "kernel size");
   static_assert(EXT <= 3, "taps beyond three words");
@@ -87,14 +91,31 @@ struct GaussQ8Op {
       }
   }
 
+  // SHIFT: win[0] is the oldest row and win[KS-2] the newest; otherwise slot = feed index mod WIN
+  __device__ __forceinline__ void push(int slot, const uint32_t (&in)[8]) {
+    if (SHIFT) {
+#pragma unroll
+      for (int i = 0; i < KS - 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) win[i][h] = win[i + 1][h];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) win[KS - 2][h] = in[h];
+    } else {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) win[slot][h] = in[h];
+    }
+  }
+
   template <int J8>
   __device__ __forceinline__ void warm(const uint4 &q) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t in[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      win[J8 & (WIN - 1)][2 * k] = __byte_perm(w[k], 0, 0x4240);
-      win[J8 & (WIN - 1)][2 * k + 1] = __byte_perm(w[k], 0, 0x4341);
+      in[2 * k] = __byte_perm(w[k], 0, 0x4240);
+      in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);
     }
+    push(J8 & (WIN - 1), in);
   }
 
   // J8 = (feed index) & 7, compile time
@@ -113,13 +134,13 @@ struct GaussQ8Op {
     for (int h = 0; h < 8; ++h) {
       uint32_t t[KS];
 #pragma unroll
-      for (int i = 0; i < KS - 1; ++i) t[i] = win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][h];  // oldest first
+      for (int i = 0; i < KS - 1; ++i) t[i] = SHIFT ? win[i][h] : win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][h];  // oldest first
       t[KS - 1] = in[h];
       const uint32_t V = sym(t, ky);  // <= 65280 per lane
       Vl[h] = V & 0x00FF00FFu;
       Vh[h] = (V >> 8) & 0x00FF00FFu;
-      win[J][h] = in[h];
     }
+    push(J, in);
     if (!FAST && !emit) return;
     uint32_t A[8], B[8];
     hpass(Vh, A);
