@@ -798,3 +798,57 @@ def test_errors_on_gpu(rcv):
     # the library is still healthy afterwards
     d = s.like()
     R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+
+
+# ---- randomized geometry sweep over the strip kernels --------------------------------------------------------
+def test_strip_kernels_random_geometries(rcv, oracle):
+    """60 random (rows, cols, channels, band height, location) draws per op family: every ragged-edge /
+    band-seam / partial-chunk combination the strip pipeline can meet, against the oracle."""
+    R = rcv
+    rng = np.random.default_rng(20261017)
+    for it in range(60):
+        h = int(rng.integers(8, 260))
+        w = int(rng.integers(8, 700))
+        cn = int(rng.integers(1, 5))
+        band = int(rng.choice([0, 4, 12, 20, 28, 36, 60]))
+        where = str(rng.choice(["device", "host"]))
+        a = rng.integers(0, 256, size=(h, w, cn), dtype=np.uint8)
+        if cn == 1:
+            a = a.reshape(h, w)
+        R.imgproc.set_option("gauss.band_rows", band)
+        try:
+            s = mats(R, a, where)
+            d = out_like(R, s, where)
+            R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+            assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), f"rand gauss5 it{it} {h}x{w}x{cn} band{band} {where}")
+            ks = int(rng.choice([3, 5, 7]))
+            sg = float(rng.uniform(0.4, 3.0))
+            d2 = out_like(R, s, where)
+            R.imgproc.gaussian_blur(s, d2, (ks, ks), sg)
+            assert_same(d2.to_numpy(), oracle.gaussian_blur(a, (ks, ks), sg, sg), f"rand gaussq8 it{it} {h}x{w}x{cn} ks{ks} s{sg:.2f} band{band}")
+            k = rng.normal(size=(3, 3)).astype(np.float32) / 2
+            R.imgproc.set_option("f2d.band_rows", band)
+            d3 = out_like(R, s, where)
+            R.imgproc.filter2d(s, d3, k, delta=1.5)
+            assert_same(d3.to_numpy(), oracle.filter2d(a, k, 1.5), f"rand filter2d u8 it{it} {h}x{w}x{cn} band{band}")
+        finally:
+            R.imgproc.set_option("gauss.band_rows", 0)
+            R.imgproc.set_option("f2d.band_rows", 0)
+        # gray f32 family
+        f = rng.random(size=(h, w), dtype=np.float32)
+        R.imgproc.set_option("sobel.band_rows", band)
+        R.imgproc.set_option("sepf32.band_rows", band)
+        try:
+            s = mats(R, f, where)
+            m = out_like(R, s, where)
+            R.imgproc.sobel_mag(s, m)
+            assert_f32(m.to_numpy(), oracle.sobel3(f)["mag"], f"rand sobel it{it} {h}x{w} band{band} {where}", max_ulp=1)
+            ks = int(rng.choice([3, 5, 7]))
+            kx = rng.normal(size=ks).astype(np.float32)
+            ky = rng.normal(size=ks).astype(np.float32)
+            d = out_like(R, s, where)
+            R.imgproc.sep_filter2d(s, d, kx, ky)
+            assert_f32(d.to_numpy(), oracle.sepfilter_f32(f, kx, ky), f"rand sepf32 it{it} {h}x{w} ks{ks} band{band}", max_ulp=0)
+        finally:
+            R.imgproc.set_option("sobel.band_rows", 0)
+            R.imgproc.set_option("sepf32.band_rows", 0)
