@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librcv_imgproc.so")
+LIB_PATH = os.environ.get("RCV_IMGPROC_LIB") or os.path.join(_HERE, "librcv_imgproc.so")
 
 RCV_OK = 0
 RCV_ERR_ARG, RCV_ERR_SIZE, RCV_ERR_DEPTH, RCV_ERR_CUDA = -1, -2, -3, -4

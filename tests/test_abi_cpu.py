@@ -60,6 +60,19 @@ def test_product_does_not_import_the_oracle():
     assert "orc_" not in out
 
 
+def test_missing_library_fails_loudly_on_first_use():
+    """The package imports (so `python -m rustcv_b200.build` works on a clean tree) but the first
+    use raises ImportError -- there is no CPU fallback to fall into."""
+    code = ("import rustcv_b200\n"
+            "try:\n"
+            "    rustcv_b200.Mat\n"
+            "except ImportError as e:\n"
+            "    assert 'no CPU fallback' in str(e); print('loud')\n")
+    env = dict(os.environ, RCV_IMGPROC_LIB="/nonexistent/librcv_imgproc.so", PYTHONPATH=ROOT)
+    out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert out.returncode == 0 and "loud" in out.stdout, out.stderr
+
+
 def _has_gpu():
     try:
         import torch
