@@ -47,7 +47,28 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "rcv_imgproc.h")]:
+        path = os.path.join(CSRC, f)
+        if os.path.isfile(path):
+            h.update(f.encode())
+            h.update(open(path, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+STAMP = LIB + ".srchash"
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    # The .so travels to the GPU box without the object files (and file times may not survive the
+    # copy): an up-to-date library is recognised by the hash of its sources, not by mtimes.
+    want = _source_hash()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
@@ -55,10 +76,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl"]
+        tmp = LIB + ".tmp"
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)  # never truncate a library another process has mapped
+    open(STAMP, "w").write(want + "\n")
     return LIB
 
 
