@@ -47,17 +47,22 @@ struct SepArgs {
 };
 
 constexpr int kSepTBX = 128, kSepTBY = 32, kSepThreads = 256;
+constexpr int kSepMaxRW = kSepTBX + (kMaxTaps - 1) * 4;  // widest raw tile row (elements)
 
+// Warp w works on tile rows w, w+8, ...; lane l on element columns l, l+32, ... : no divisions in
+// the loops (the reflected source offset of every raw-tile column is computed once per thread),
+// conflict-free shared-memory rows, coalesced global rows.
 template <typename T>
 __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const SepArgs<T> a) {
   typedef typename SepTraits<T>::Acc Acc;
   extern __shared__ __align__(16) uint8_t smem[];
   const int rx = a.kw / 2, ry = a.kh / 2;
-  const int halo_x = (a.kw - 1) * a.cn;
-  const int RW = kSepTBX + halo_x;     // raw tile width (elements)
-  const int RH = kSepTBY + a.kh - 1;   // raw tile height
+  const int RW = kSepTBX + (a.kw - 1) * a.cn;  // raw tile width (elements)
+  const int RH = kSepTBY + a.kh - 1;           // raw tile height
   T *raw = (T *)smem;
   Acc *mid = (Acc *)(smem + (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NWARP = kSepThreads / 32;
 
   const int ncols = a.cols * a.cn;
   const int ex0 = blockIdx.x * kSepTBX;  // first element column of the tile
@@ -65,47 +70,64 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const SepArgs<T> a) {
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
 
-  // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][reflect_px(ex0 + x - rx*cn)]
-  for (int i = threadIdx.x; i < RW * RH; i += kSepThreads) {
-    int r = i / RW, x = i - r * RW;
-    int ex = ex0 + x - rx * a.cn;
-    // floor division for negatives
-    int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
-    int ch = ex - px * a.cn;
-    int sy = reflect101(y0 + r - ry, a.rows);
-    int sx = reflect101(px, a.cols);
-    raw[i] = ((const T *)(src + (size_t)sy * a.sstep))[sx * a.cn + ch];
+  // source element offset of raw-tile column lane + 32*i (REFLECT_101 on the pixel index)
+  constexpr int NX = (kSepMaxRW + 31) / 32;
+  int xoff[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    const int x = lane + 32 * i;
+    const int ex = ex0 + x - rx * a.cn;
+    const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);  // floor division
+    xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+  }
+  // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][xoff(x)]
+  for (int r = warp; r < RH; r += NWARP) {
+    const T *srow = (const T *)(src + (size_t)reflect101(y0 + r - ry, a.rows) * a.sstep);
+    T *rrow = raw + r * RW;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const int x = lane + 32 * i;
+      if (x < RW) rrow[x] = srow[xoff[i]];
+    }
   }
   __syncthreads();
   // stage 2: horizontal
-  for (int i = threadIdx.x; i < kSepTBX * RH; i += kSepThreads) {
-    int r = i / kSepTBX, x = i - r * kSepTBX;
-    const T *p = raw + r * RW + x;
-    Acc acc = 0;
-    for (int j = 0; j < a.kw; ++j) {
-      if (sizeof(T) == 1)
-        acc += (Acc)a.kx[j] * (Acc)p[j * a.cn];
-      else
-        acc = fmaf((float)a.kx[j], (float)p[j * a.cn], (float)acc);
+  for (int r = warp; r < RH; r += NWARP) {
+#pragma unroll
+    for (int i = 0; i < kSepTBX / 32; ++i) {
+      const int x = lane + 32 * i;
+      const T *p = raw + r * RW + x;
+      Acc acc = 0;
+      for (int j = 0; j < a.kw; ++j) {
+        if (sizeof(T) == 1)
+          acc += (Acc)a.kx[j] * (Acc)p[j * a.cn];
+        else
+          acc = fmaf((float)a.kx[j], (float)p[j * a.cn], (float)acc);
+      }
+      mid[r * kSepTBX + x] = acc;
     }
-    mid[i] = acc;
   }
   __syncthreads();
   // stage 3: vertical
-  for (int i = threadIdx.x; i < kSepTBX * kSepTBY; i += kSepThreads) {
-    int r = i / kSepTBX, x = i - r * kSepTBX;
-    int y = y0 + r, ex = ex0 + x;
-    if (y >= a.rows || ex >= ncols) continue;
-    const Acc *p = mid + r * kSepTBX + x;
-    if (sizeof(T) == 1) {
-      uint32_t acc = 32768u;
-      for (int k = 0; k < a.kh; ++k) acc += (uint32_t)a.ky[k] * (uint32_t)p[k * kSepTBX];
-      acc >>= 16;
-      ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)(acc > 255u ? 255u : acc);
-    } else {
-      float acc = 0.0f;
-      for (int k = 0; k < a.kh; ++k) acc = fmaf((float)a.ky[k], (float)p[k * kSepTBX], acc);
-      ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+  for (int r = warp; r < kSepTBY; r += NWARP) {
+    const int y = y0 + r;
+    if (y >= a.rows) break;
+#pragma unroll
+    for (int i = 0; i < kSepTBX / 32; ++i) {
+      const int x = lane + 32 * i;
+      const int ex = ex0 + x;
+      if (ex >= ncols) continue;
+      const Acc *p = mid + r * kSepTBX + x;
+      if (sizeof(T) == 1) {
+        uint32_t acc = 32768u;
+        for (int k = 0; k < a.kh; ++k) acc += (uint32_t)a.ky[k] * (uint32_t)p[k * kSepTBX];
+        acc >>= 16;
+        ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)(acc > 255u ? 255u : acc);
+      } else {
+        float acc = 0.0f;
+        for (int k = 0; k < a.kh; ++k) acc = fmaf((float)a.ky[k], (float)p[k * kSepTBX], acc);
+        ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+      }
     }
   }
 }
@@ -281,6 +303,7 @@ struct F2dArgs {
 };
 
 constexpr int kF2dTBX = 64, kF2dTBY = 16, kF2dThreads = 256;
+constexpr int kF2dMaxRW = kF2dTBX + (kMaxTaps - 1) * 4;
 
 template <typename T>
 __global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
@@ -290,36 +313,52 @@ __global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
   const int RH = kF2dTBY + a.kh - 1;
   float *taps = (float *)smem;
   T *raw = (T *)(smem + (((size_t)a.kw * a.kh * 4 + 15) & ~(size_t)15));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NWARP = kF2dThreads / 32;
   const int ncols = a.cols * a.cn;
   const int ex0 = blockIdx.x * kF2dTBX, y0 = blockIdx.y * kF2dTBY;
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
   for (int i = threadIdx.x; i < a.kw * a.kh; i += kF2dThreads) taps[i] = a.taps[i];
-  for (int i = threadIdx.x; i < RW * RH; i += kF2dThreads) {
-    int r = i / RW, x = i - r * RW;
-    int ex = ex0 + x - rx * a.cn;
-    int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
-    int ch = ex - px * a.cn;
-    int sy = reflect101(y0 + r - ry, a.rows);
-    int sx = reflect101(px, a.cols);
-    raw[i] = ((const T *)(src + (size_t)sy * a.sstep))[sx * a.cn + ch];
+  constexpr int NX = (kF2dMaxRW + 31) / 32;
+  int xoff[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    const int x = lane + 32 * i;
+    const int ex = ex0 + x - rx * a.cn;
+    const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
+    xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+  }
+  for (int r = warp; r < RH; r += NWARP) {
+    const T *srow = (const T *)(src + (size_t)reflect101(y0 + r - ry, a.rows) * a.sstep);
+    T *rrow = raw + r * RW;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const int x = lane + 32 * i;
+      if (x < RW) rrow[x] = srow[xoff[i]];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kF2dTBX * kF2dTBY; i += kF2dThreads) {
-    int r = i / kF2dTBX, x = i - r * kF2dTBX;
-    int y = y0 + r, ex = ex0 + x;
-    if (y >= a.rows || ex >= ncols) continue;
-    float acc = a.delta;
-    for (int ki = 0; ki < a.kh; ++ki) {
-      const T *p = raw + (r + ki) * RW + x;
-      const float *t = taps + ki * a.kw;
-      for (int kj = 0; kj < a.kw; ++kj) acc = fmaf(t[kj], (float)p[kj * a.cn], acc);
-    }
-    if (sizeof(T) == 1) {
-      int v = __float2int_rn(acc);  // round half to even, saturating conversion
-      ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)min(max(v, 0), 255);
-    } else {
-      ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+  for (int r = warp; r < kF2dTBY; r += NWARP) {
+    const int y = y0 + r;
+    if (y >= a.rows) break;
+#pragma unroll
+    for (int i = 0; i < kF2dTBX / 32; ++i) {
+      const int x = lane + 32 * i;
+      const int ex = ex0 + x;
+      if (ex >= ncols) continue;
+      float acc = a.delta;
+      for (int ki = 0; ki < a.kh; ++ki) {
+        const T *p = raw + (r + ki) * RW + x;
+        const float *t = taps + ki * a.kw;
+        for (int kj = 0; kj < a.kw; ++kj) acc = fmaf(t[kj], (float)p[kj * a.cn], acc);
+      }
+      if (sizeof(T) == 1) {
+        int v = __float2int_rn(acc);  // round half to even, saturating conversion
+        ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)min(max(v, 0), 255);
+      } else {
+        ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+      }
     }
   }
 }
