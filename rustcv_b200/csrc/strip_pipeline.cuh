@@ -276,17 +276,17 @@ static inline bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) 
 // tens of MB (TLB reach, L2-resident halo rows) instead of hundreds.  36 rows (40 fed rows =
 // 5 chunks of R) measured best for the 5x5 Gaussian: 8.04 us per 4K frame vs 8.64 at 60 rows
 // and 10.9 at 244.  Tiny jobs use shorter bands to occupy more warps.
-static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv) {
+static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv, int nw = kNW) {
   int64_t forced = opt_get(optname, 0);
   if (forced > 0) return (int)forced;
-  const long long warps = (long long)ctx_sm_count(c) * kNW;
+  const long long warps = (long long)ctx_sm_count(c) * nw;
   int br = 5 * kR - 2 * hv;
   const long long items = (long long)strips * n * ((rows + br - 1) / br);
   if (items < warps) br = 4 * kR - 2 * hv;
   return br;
 }
 
-template <class Op>
+template <class Op, int S = kS, int NW = kNW>
 static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout, const char *band_opt,
                         cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr,
                         const float *ftaps = nullptr, int nftaps = 0) {
@@ -306,7 +306,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   p.rows = src.v.rows;
   p.row_bytes = (int)src.v.row_bytes();
   p.strips = ceil_div(p.row_bytes, kOutBytes);
-  p.band_rows = pick_band_rows(c, band_opt, p.rows, p.strips, src.n, Op::HV);
+  p.band_rows = pick_band_rows(c, band_opt, p.rows, p.strips, src.n, Op::HV, NW);
   p.bands = ceil_div(p.rows, p.band_rows);
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
@@ -317,20 +317,20 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   }
   for (int i = 0; i < 52; ++i) p.ftaps[i] = (ftaps && i < nftaps) ? ftaps[i] : 0.0f;
 
-  auto kern = k_strip<Op, kR, kS, kNW>;
-  const int smem = kNW * kS * kR * kTileBytes + kNW * kS * 8;
+  auto kern = k_strip<Op, kR, S, NW>;
+  const int smem = NW * S * kR * kTileBytes + NW * S * 8;
   RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  long long blocks = (p.total_items + kNW - 1) / kNW;
+  long long blocks = (p.total_items + NW - 1) / NW;
   int64_t grid_opt = opt_get("strip.grid", 0);
   int grid = (int)(blocks < ctx_sm_count(c) ? blocks : ctx_sm_count(c));
   if (grid_opt > 0) grid = (int)grid_opt;
-  if (opt_get("strip.dynamic", 1) != 0 && p.total_items > (long long)grid * kNW) {
+  if (opt_get("strip.dynamic", 1) != 0 && p.total_items > (long long)grid * NW) {
     void *ctr = nullptr;
     RCV_TRY(ctx_scratch(c, SCR_COUNTER, sizeof(unsigned long long), &ctr));
     RCV_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
     p.next_item = (unsigned long long *)ctr;
   }
-  kern<<<grid, kNW * 32, smem, s>>>(tmap, p);
+  kern<<<grid, NW * 32, smem, s>>>(tmap, p);
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;

@@ -26,7 +26,7 @@ for i in range(NF):
     F.check(F.lib.rcv_mat_upload(C.byref(host.c()), C.byref(src[i].c())))
 stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(0))
 R.imgproc.set_blocking(False)
-ALL = ["gauss.band_rows", "strip.dynamic", "strip.grid"]
+ALL = ["gauss.band_rows", "strip.dynamic", "strip.grid", "gauss.variant"]
 
 
 def run(cfg: str, steps=20):
