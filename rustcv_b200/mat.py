@@ -191,6 +191,12 @@ class Mat:
             F.check(F.lib.rcv_pinned_free(self._pinned_ptr))
             self._pinned_ptr = None
 
+    def __del__(self):  # device / pinned storage is owned by the Mat (a Rust Drop would call the same frees)
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001  (interpreter shutdown, context already gone)
+            pass
+
     def __repr__(self) -> str:  # mat.rs:56-64
         return (f"Mat {{ rows: {self.rows}, cols: {self.cols}, channels: {self.channels}, step: {self.step}, "
                 f"depth: {self.depth}, loc: {self.loc} }}")
@@ -219,5 +225,13 @@ class MatBatch:
 
     def free(self) -> None:
         if self.owned and self.n:
-            F.check(F.lib.rcv_mat_free_device_batch(self.arr, self.n))
             self.owned = False
+            for m in self.mats:
+                m.data = None
+            F.check(F.lib.rcv_mat_free_device_batch(self.arr, self.n))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001
+            pass

@@ -32,6 +32,14 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert exported == declared, (set(declared) ^ set(exported))
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 and as C++ with no other includes."""
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        r = subprocess.run(["gcc", "-x", lang, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", HEADER],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_ctypes_binding_covers_the_header():
     from rustcv_b200 import _ffi
 

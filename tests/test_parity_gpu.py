@@ -70,9 +70,19 @@ def upload_into(R, a, dev_mat):
 
 
 def out_like(R, src, where, channels=None, depth=None, rows=None, cols=None):
+    """A zero-filled destination in the same kind of storage (ops that leave pixels untouched -- the
+    odd last column of a YUYV row -- are compared against the oracle's zero-initialised output)."""
     if where == "host":
         return R.Mat.empty()
-    return src.like(channels=channels, depth=depth, rows=rows, cols=cols)
+    m = src.like(channels=channels, depth=depth, rows=rows, cols=cols)
+    if where == "pinned":
+        m.data[:] = 0
+    else:
+        z = R.Mat.new(m.rows, m.cols, m.channels, m.depth)
+        if m.rows and m.cols:
+            from rustcv_b200 import _ffi as F
+            F.check(F.lib.rcv_mat_upload(C.byref(z.c()), C.byref(m.c())))
+    return m
 
 
 WHERE = ["host", "device", "pinned"]
@@ -852,3 +862,27 @@ def test_strip_kernels_random_geometries(rcv, oracle):
         finally:
             R.imgproc.set_option("sobel.band_rows", 0)
             R.imgproc.set_option("sepf32.band_rows", 0)
+
+
+def test_two_devices_in_one_process(rcv, oracle):
+    """One context per GPU: Mats are routed by RcvMat.device (skipped on a single-GPU box)."""
+    import ctypes as C2
+
+    R = rcv
+    from rustcv_b200 import _ffi as F
+
+    n = C2.c_int()
+    F.check(F.lib.rcv_device_count(C2.byref(n)))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    R.imgproc.init(1)
+    a = oracle.fill_u8(200, 120 * 500 * 3).reshape(120, 500, 3)
+    want = oracle.gaussian_blur(a, (5, 5))
+    s1 = R.Mat.from_numpy(a).upload(device=1)
+    assert s1.device == 1
+    d1 = s1.like()
+    R.imgproc.gaussian_blur(s1, d1, (5, 5), 0.0)
+    assert_same(d1.to_numpy(), want, "device 1")
+    s0 = R.Mat.from_numpy(a).upload(device=0)
+    with pytest.raises(F.RcvError):
+        R.imgproc.gaussian_blur(s0, d1, (5, 5), 0.0)  # Mats on different GPUs
