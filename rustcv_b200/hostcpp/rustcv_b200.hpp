@@ -236,5 +236,35 @@ inline Result decode_frame(const uint8_t *data, size_t len, uint32_t width, uint
   return Result();
 }
 
+// Device-resident form: only the raw frame crosses PCIe (2 B/px for
+// YUYV), the conversion runs on the GPU and the BGR stays in HBM for the imgproc calls that follow.
+// `mat` must already be height x width x 3.  stride = bytes between source rows (0 = packed).
+inline Result decode_frame(const uint8_t *data, size_t len, uint32_t width, uint32_t height, uint32_t fcc,
+                           core::DeviceMat &mat, size_t stride = 0) {
+  const int bpp = fcc == YUYV ? 2 : fcc == BGRA ? 4 : 0;
+  Result r;
+  if (!bpp) {
+    r.code = RCV_ERR_UNSUPPORTED;
+    r.message = "format not converted on this path";
+    return r;
+  }
+  if (!stride) stride = (size_t)width * bpp;
+  if (height && len < (size_t)(height - 1) * stride + (size_t)width * bpp) {
+    r.code = RCV_ERR_SIZE;
+    r.message = "frame buffer shorter than height x stride";
+    return r;
+  }
+  RcvMat src;
+  std::memset(&src, 0, sizeof(src));
+  src.data = const_cast<uint8_t *>(data);
+  src.rows = (int32_t)height;
+  src.cols = (int32_t)width;
+  src.step = stride;
+  src.channels = (uint8_t)bpp;
+  src.depth = RCV_U8;
+  src.loc = RCV_HOST;
+  return check(rcv_cvt_color(&src, &mat.pod(), fcc == YUYV ? RCV_COLOR_YUYV2BGR : RCV_COLOR_BGRA2BGR));
+}
+
 }  // namespace videoio
 }  // namespace rustcv

@@ -43,11 +43,18 @@ def decode_frame(data: np.ndarray, width: int, height: int, fcc: int, mat: Mat, 
     data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
     if mat.loc == F.RCV_HOST:
         mat.ensure_size(height, width, 3, U8)  # videoio/mod.rs:192-199
-    if fcc in (YUYV, BGRA) and stride is None:
+    elif (mat.rows, mat.cols, mat.channels) != (height, width, 3):
+        raise F.RcvError(F.RCV_ERR_SIZE, "a device / pinned Mat must already be height x width x 3")
+    # A device-resident `mat`: only the RAW frame crosses PCIe (2 B/px for
+    # YUYV instead of 3 B/px of BGR), the conversion runs on the GPU and the BGR stays in HBM for the
+    # imgproc calls that follow.  Row-wise form; identical to the packed run whenever width is even.
+    packed_ok = mat.loc != F.RCV_DEVICE and mat.step == width * 3
+    if fcc in (YUYV, BGRA) and stride is None and packed_ok:
         fn = F.lib.rcv_yuyv_to_bgr_packed if fcc == YUYV else F.lib.rcv_bgra_to_bgr_packed
-        assert mat.loc != F.RCV_DEVICE and mat.step == width * 3
         F.check(fn(data.ctypes.data, data.size, mat.data.ctypes.data, mat.data.size, width, height))
         return True
+    if fcc == YUYV and stride is None and (width & 1):
+        raise F.RcvError(F.RCV_ERR_UNSUPPORTED, "odd-width packed YUYV pairs straddle rows: use a packed host Mat")
     bpp = {YUYV: 2, UYVY: 2, BGRA: 4, RGB3: 3, BGR3: 3}.get(fcc)
     if bpp is None:
         return False
@@ -57,6 +64,9 @@ def decode_frame(data: np.ndarray, width: int, height: int, fcc: int, mat: Mat, 
     src = Mat()
     src.data, src.rows, src.cols, src.step, src.channels, src.depth = data, height, width, step, bpp, U8
     if fcc == BGR3:  # "Assume RGB/BGR or copy" (videoio/mod.rs:253-257)
+        if mat.loc == F.RCV_DEVICE:
+            F.check(F.lib.rcv_mat_upload(C.byref(src.c()), C.byref(mat.c())))
+            return True
         for r in range(height):
             mat.row_bytes(r)[:] = src.row_bytes(r)
         return True

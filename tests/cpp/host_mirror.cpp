@@ -53,6 +53,18 @@ int main(int argc, char **argv) {
     EXPECT(std::memcmp(m.data.data(), want.data(), want.size()) == 0);
     EXPECT(orc_crc32(m.data.data(), m.data.size()) == 0x0BF66518u);
   }
+  // read() into a device-resident Mat: raw YUYV up (2 B/px), BGR stays in HBM
+  {
+    std::vector<uint8_t> src(640 * 480 * 2);
+    orc_fill_u8(1, src.data(), src.size());
+    core::DeviceMat dm;
+    EXPECT(core::DeviceMat::create(dm, 480, 640, 3).is_ok());
+    EXPECT(videoio::decode_frame(src.data(), src.size(), 640, 480, videoio::YUYV, dm).is_ok());
+    core::Mat back;
+    EXPECT(dm.download(back).is_ok());
+    EXPECT(orc_crc32(back.data.data(), back.data.size()) == 0x0BF66518u);
+    EXPECT(videoio::decode_frame(src.data(), 100, 640, 480, videoio::YUYV, dm).code == RCV_ERR_SIZE);
+  }
   // GaussianBlur 5x5 on host Mats and on device-resident Mats
   {
     core::Mat src = core::Mat::create(270, 480, 3), dst, want = core::Mat::create(270, 480, 3);

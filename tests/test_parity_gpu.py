@@ -886,3 +886,27 @@ def test_two_devices_in_one_process(rcv, oracle):
     s0 = R.Mat.from_numpy(a).upload(device=0)
     with pytest.raises(F.RcvError):
         R.imgproc.gaussian_blur(s0, d1, (5, 5), 0.0)  # Mats on different GPUs
+
+
+def test_decode_frame_into_device_mat_then_process(rcv, oracle):
+    """read() with a device-resident Mat: the raw YUYV frame is uploaded (2 B/px), converted on the GPU,
+    and the BGR stays in HBM for the blur that follows; only the final result comes back."""
+    R = rcv
+    w, h = 640, 480
+    raw = oracle.fill_u8(1, w * h * 2)
+    frame = R.Mat.device_new(h, w, 3)
+    assert R.videoio.decode_frame(raw, w, h, R.videoio.YUYV, frame)
+    assert oracle.crc32(frame.to_numpy()) == 0x0BF66518
+    blurred = frame.like()
+    R.imgproc.gaussian_blur(frame, blurred, (5, 5), 0.0)
+    want = oracle.gaussian_blur(oracle.yuyv_to_bgr(raw.reshape(h, w, 2)), (5, 5))
+    assert_same(blurred.to_numpy(), want, "decode -> blur on device")
+    # strided source rows (Frame.stride, ignored by the reference's facade)
+    padded = np.full((h, w * 2 + 64), 0xEE, np.uint8)
+    padded[:, : w * 2] = raw.reshape(h, w * 2)
+    assert R.videoio.decode_frame(padded, w, h, R.videoio.YUYV, frame, stride=w * 2 + 64)
+    assert oracle.crc32(frame.to_numpy()) == 0x0BF66518
+    # BGR passthrough upload
+    bgr = oracle.fill_u8(9, w * h * 3)
+    assert R.videoio.decode_frame(bgr, w, h, R.videoio.BGR3, frame)
+    assert (frame.to_numpy().ravel() == bgr).all()
