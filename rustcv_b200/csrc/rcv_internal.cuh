@@ -80,6 +80,7 @@ struct Ctx {
   cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {};
   void *scratch[SCR_COUNT] = {};
   size_t scratch_bytes[SCR_COUNT] = {};
+  unsigned counter_parity = 0;       // which of the two strip-kernel work counters the next launch uses
   int resize_key[4] = {0, 0, 0, 0};  // geometry of the resize tables currently in SCR_TABLE_X/Y
   std::mutex mu;
 };

@@ -51,6 +51,7 @@ struct StripParams {
   int vec_store;  // all outputs 16-byte aligned (base, step, frame stride)
   long long total_items;
   unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
+  unsigned long long *reset_item; // the OTHER counter of the pair: zeroed here for the next launch on this stream
   uint32_t taps_x[4], taps_y[4];  // GaussQ8Op: symmetric Q8 taps, [0] outermost .. [KS/2] centre
   float ftaps[52];                // SepF32Op: kx[0..KS) then ky[0..KS); Filter2dOp: KS*KS taps row-major, then delta
 };
@@ -70,6 +71,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   const uint32_t tiles = smem_u32(smem_raw) + (uint32_t)warp * S * kStageBytes;
   const uint32_t bars = smem_u32(smem_raw) + (uint32_t)NW * S * kStageBytes + (uint32_t)warp * S * 8;
 
+  // Two work counters alternate between launches: this launch claims from one and clears the other,
+  // which the next launch on the (single, in-order) library stream will use -- no memset node.
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_item != nullptr) *p.reset_item = 0ULL;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(bars + s * 8, 1);
@@ -311,6 +315,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
   p.next_item = nullptr;
+  p.reset_item = nullptr;
   for (int i = 0; i < 4; ++i) {
     p.taps_x[i] = taps_x ? (uint32_t)taps_x[i] : 0;
     p.taps_y[i] = taps_y ? (uint32_t)taps_y[i] : 0;
@@ -319,16 +324,24 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
 
   auto kern = k_strip<Op, kR, S, NW>;
   const int smem = NW * S * kR * kTileBytes + NW * S * 8;
-  RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_done[16] = {};  // per template instantiation, per device
+  const int dev = ctx_device(c) & 15;
+  if (!attr_done[dev]) {
+    RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[dev] = true;
+  }
   long long blocks = (p.total_items + NW - 1) / NW;
   int64_t grid_opt = opt_get("strip.grid", 0);
   int grid = (int)(blocks < ctx_sm_count(c) ? blocks : ctx_sm_count(c));
   if (grid_opt > 0) grid = (int)grid_opt;
   if (opt_get("strip.dynamic", 1) != 0 && p.total_items > (long long)grid * NW) {
     void *ctr = nullptr;
-    RCV_TRY(ctx_scratch(c, SCR_COUNTER, sizeof(unsigned long long), &ctr));
-    RCV_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-    p.next_item = (unsigned long long *)ctr;
+    const bool fresh = c->scratch_bytes[SCR_COUNTER] == 0;
+    RCV_TRY(ctx_scratch(c, SCR_COUNTER, 2 * sizeof(unsigned long long), &ctr));
+    if (fresh) RCV_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), s));
+    const unsigned which = c->counter_parity++ & 1u;
+    p.next_item = (unsigned long long *)ctr + which;
+    p.reset_item = (unsigned long long *)ctr + (which ^ 1u);
   }
   kern<<<grid, NW * 32, smem, s>>>(tmap, p);
   count_launch();
