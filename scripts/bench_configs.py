@@ -1,6 +1,9 @@
 """Device-resident timing of BASELINE.json configs 1, 3, 4, 5 (config 2 is bench.py).
-One JSON line per config: Mpix/s, algorithmic GB/s, fraction of the measured HBM peak.
+One JSON line per config: Mpix/s, algorithmic GB/s, fraction of the measured HBM peak, and (N=1, rank 0,
+CPU=1 in the environment) the CPU oracle timed beside it at 1 thread and at all host threads.
 GPU box only:  python scripts/bench_configs.py [cfg ...]
+               python -m torch.distributed.run --nproc-per-node N ... scripts/bench_configs.py cfg4full cfg5full
+(cfg4full / cfg5full use BASELINE.json's batch sizes -- 256 / 64 frames -- sharded frame j -> rank j mod N.)
 """
 import ctypes as C
 import json
@@ -16,14 +19,39 @@ import rustcv_b200 as R  # noqa: E402
 from oracle import pyoracle as O  # noqa: E402
 from rustcv_b200 import _ffi as F  # noqa: E402
 
+import time  # noqa: E402
+
+import torch.distributed as dist  # noqa: E402
+
 PEAK = 6549.4
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-R.imgproc.init(0)
-stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(0))
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(LOCAL)
+if WORLD > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+R.imgproc.init(LOCAL)
+stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(LOCAL), device=torch.device("cuda", LOCAL))
 R.imgproc.set_blocking(False)
+CPU = os.environ.get("CPU", "0") == "1" and WORLD == 1
+
+
+def cpu_time(fn, reps):
+    """seconds per call of an oracle function, 1 thread and all host threads"""
+    out = {}
+    for label, nt in (("1t", 1), ("nt", len(os.sched_getaffinity(0)))):
+        O.set_threads(nt)
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        out[label] = (time.perf_counter() - t0) / reps
+    O.set_threads(1)
+    out["threads"] = len(os.sched_getaffinity(0))
+    return out
 
 
 def fill_batch(batch, make):
@@ -37,22 +65,32 @@ def fill_batch(batch, make):
 def timeit(fn, steps=20, warm=3):
     for _ in range(warm):
         fn()
-    R.imgproc.sync(0)
+    R.imgproc.sync(LOCAL)
+    if WORLD > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         fn()
     e1.record(stream)
-    R.imgproc.sync(0)
-    return e0.elapsed_time(e1) / steps
+    R.imgproc.sync(LOCAL)
+    ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:  # max over ranks
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def report(name, ms, units, bytes_per_unit, extra=None):
+    """units = units processed per step by THIS rank; the line reports the whole job (all ranks)."""
     gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
-    line = {"config": name, "ms_per_step": ms, "units_per_step": units, "Munits_per_s": units / ms / 1e3,
-            "algorithmic_bytes_per_unit": bytes_per_unit, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / PEAK}
+    line = {"config": name, "n_gpus": WORLD, "ms_per_step": ms, "units_per_step": units * WORLD,
+            "Munits_per_s": units * WORLD / ms / 1e3, "algorithmic_bytes_per_unit": bytes_per_unit,
+            "achieved_GBps_per_gpu": gbs, "frac_of_measured_hbm_peak": gbs / PEAK}
     line.update(extra or {})
-    print(json.dumps(line), flush=True)
+    if RANK == 0:
+        print(json.dumps(line), flush=True)
 
 
 def cfg1():
@@ -62,7 +100,13 @@ def cfg1():
     fill_batch(src, lambda i: np.roll(base, i * 31).reshape(h, w, 2))
     ms = timeit(lambda: R.imgproc.cvt_color_batch(src, dst, R.imgproc.COLOR_YUYV2BGR))
     ok = O.crc32(dst[0].to_numpy()) == 0x0BF66518
-    report("cfg1 YUYV->BGR 640x480 x256", ms, n * h * w, 5, {"crc_ok": ok})
+    extra = {"crc_ok": ok}
+    if CPU:  # the reference's own loop is single-threaded (videoio/mod.rs:344-371); the facade port is its restatement
+        t0 = time.perf_counter()
+        for _ in range(200):
+            O.yuyv_to_bgr_facade(base, w, h)
+        extra["cpu_ref_restated_1t_Mpix_s"] = 200 * h * w / (time.perf_counter() - t0) / 1e6
+    report("cfg1 YUYV->BGR 640x480 x256", ms, n * h * w, 5, extra)
     src.free(); dst.free()
 
 
@@ -76,34 +120,53 @@ def cfg3():
     want = O.sobel3(base.reshape(h, w))["mag"]
     O.set_threads(1)
     ok = bool((np.abs(dst[0].to_numpy() - want) <= 1e-6).all())
-    report("cfg3 Sobel3x3+magnitude 1920x1080 f32 x64", ms, n * h * w, 8, {"parity_frame0": ok})
+    extra = {"parity_frame0": ok}
+    if CPU:
+        img = base.reshape(h, w)
+        c = cpu_time(lambda: O.sobel3(img), 8)
+        extra.update({"cpu_oracle_1t_Mpix_s": h * w / c["1t"] / 1e6, "cpu_oracle_nt_Mpix_s": h * w / c["nt"] / 1e6, "cpu_threads": c["threads"]})
+    report("cfg3 Sobel3x3+magnitude 1920x1080 f32 x64", ms, n * h * w, 8, extra)
     src.free(); dst.free()
 
 
-def cfg4():
-    n, h, w = 16, 4320, 7680
+def cfg4(n=16):
+    n, h, w = max(1, n // WORLD), 4320, 7680
     src, dst = R.Mat.device_batch(n, h, w, 3), R.Mat.device_batch(n, h // 4, w // 4, 3)
     base = O.fill_u8(4, h * w * 3)
     fill_batch(src, lambda i: (np.roll(base, i * 31) if i else base).reshape(h, w, 3))
     ms = timeit(lambda: R.imgproc.resize_batch(src, dst), steps=10)
-    ok = O.crc32(dst[0].to_numpy()) == 0x31A84A85
-    report("cfg4 resize 7680x4320->1920x1080 BGR u8 x16", ms, n * (h // 4) * (w // 4), 15,
-           {"crc_ok": ok, "sector_floor_bytes_per_unit": 27,
-            "frac_vs_sector_floor": n * (h // 4) * (w // 4) * 27 / (ms * 1e-3) / 1e9 / PEAK})
+    ok = (O.crc32(dst[0].to_numpy()) == 0x31A84A85) if RANK == 0 else None
+    extra = {"crc_ok": ok, "frames_per_gpu": n, "sector_floor_bytes_per_unit": 27, "full_source_bytes_per_unit": 51,
+             "frac_vs_sector_floor": n * (h // 4) * (w // 4) * 27 / (ms * 1e-3) / 1e9 / PEAK}
+    if CPU:
+        img = base.reshape(h, w, 3)
+        c = cpu_time(lambda: O.resize_bilinear(img, h // 4, w // 4), 4)
+        px = (h // 4) * (w // 4)
+        extra.update({"cpu_oracle_1t_Mpix_s": px / c["1t"] / 1e6, "cpu_oracle_nt_Mpix_s": px / c["nt"] / 1e6, "cpu_threads": c["threads"]})
+    report(f"cfg4 resize 7680x4320->1920x1080 BGR u8 x{n * WORLD}", ms, n * (h // 4) * (w // 4), 15, extra)
     src.free(); dst.free()
 
 
-def cfg5():
-    n, s = 8, 4096
+def cfg5(n=8):
+    n, s = max(1, n // WORLD), 4096
     src, dst = R.Mat.device_batch(n, s, s, 1, R.F32), R.Mat.device_batch(n, s, s, 1, R.F32)
     base = O.fill_f32(5, s * s)
     fill_batch(src, lambda i: (np.roll(base, i * 31) if i else base).reshape(s, s))
     M = R.imgproc.get_rotation_matrix_2d(((s - 1) / 2, (s - 1) / 2), 15.0)
     ms = timeit(lambda: R.imgproc.warp_affine_batch(src, dst, M), steps=10)
-    report("cfg5 warpAffine 15deg 4096x4096 f32 x8", ms, n * s * s, 7.6)
+    extra = {"frames_per_gpu": n}
+    if CPU:
+        img = base.reshape(s, s)
+        c = cpu_time(lambda: O.warp_affine(img, M.ravel()), 2)
+        extra.update({"cpu_oracle_1t_Mpix_s": s * s / c["1t"] / 1e6, "cpu_oracle_nt_Mpix_s": s * s / c["nt"] / 1e6, "cpu_threads": c["threads"]})
+    report(f"cfg5 warpAffine 15deg 4096x4096 f32 x{n * WORLD}", ms, n * s * s, 7.6, extra)
     src.free(); dst.free()
 
 
-ALL = {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
-for name in (sys.argv[1:] or list(ALL)):
+ALL = {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
+       "cfg4full": lambda: cfg4(256), "cfg5full": lambda: cfg5(64)}
+for name in (sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]):
     ALL[name]()
+if WORLD > 1:
+    dist.barrier()
+    dist.destroy_process_group()
