@@ -307,11 +307,14 @@ __device__ __forceinline__ void warp_pixel(const WarpTileArgs &t, uint32_t tile,
                                            const uint8_t *src, T *out) {
   constexpr int E = CN * (int)sizeof(T);  // bytes per pixel
   const WarpArgs &a = t.a;
-  const float flx = floorf(sx), fly = floorf(sy);
+  // floor through the integer: F2I.FLOOR + I2FP (ALU pipe) instead of FRND.FLOOR + F2I (two conversion-
+  // pipe ops).  Identical to floorf for every finite |s| < 2^31; beyond that F2I saturates, which the
+  // in-image test below rejects exactly like the oracle's float comparison does.
+  int ix = __float2int_rd(sx), iy = __float2int_rd(sy);
+  const float flx = __int2float_rn(ix), fly = __int2float_rn(iy);
   const float fx = __fsub_rn(sx, flx), fy = __fsub_rn(sy, fly);
   const int rowb = t.bw * 4;  // box row pitch in bytes
   bool inside = true, x0ok = true, x1ok = true, y0ok = true, y1ok = true, inbox = true;
-  int ix = (int)flx, iy = (int)fly;
   if (!INTERIOR) {
     inside = flx >= -1.0f && flx < (float)a.scols && fly >= -1.0f && fly < (float)a.srows;
     ix = inside ? ix : 0;
@@ -447,9 +450,60 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
   }
 }
 
+// Simulates the tap addresses of a few warps (32 consecutive dst x) and returns the pitch, among
+// min_words rounded up to 4 plus {0, 4, .., 28}, with the fewest shared-memory wavefronts per load.
+static int pick_box_pitch(int min_words, int E, double m0, double m3) {
+  // the answer depends on the matrix only: remember the last one (a capture loop warps with one matrix)
+  static thread_local struct { double m0, m3; int e, mw, bw; } last = {0, 0, 0, 0, 0};
+  if (last.bw && last.m0 == m0 && last.m3 == m3 && last.e == E && last.mw == min_words) return last.bw;
+  const int base = (min_words + 3) & ~3;
+  int best = base;
+  long best_cost = -1;
+  for (int add = 0; add < 32; add += 4) {
+    const int rowb = (base + add) * 4;
+    long cost = 0;
+    for (int trial = 0; trial < 12; ++trial) {
+      int word[32];
+      for (int l = 0; l < 32; ++l) {
+        const double sx = m0 * (37 * trial + l) + 0.37 * trial, sy = m3 * (37 * trial + l) + 0.61 * trial;
+        const long addr = (long)floor(sy) * rowb + (long)floor(sx) * E;
+        word[l] = (int)(addr >> 2);  // arithmetic shift: floor for negatives
+      }
+      int worst = 1;
+      for (int bank = 0; bank < 32; ++bank) {
+        int distinct = 0, seen[32];
+        for (int l = 0; l < 32; ++l) {
+          if ((word[l] & 31) != bank) continue;
+          bool dup = false;
+          for (int k = 0; k < distinct; ++k) dup |= seen[k] == word[l];
+          if (!dup) seen[distinct++] = word[l];
+        }
+        if (distinct > worst) worst = distinct;
+      }
+      cost += worst;
+    }
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = base + add;
+    }
+  }
+  last.m0 = m0;
+  last.m3 = m3;
+  last.e = E;
+  last.mw = min_words;
+  last.bw = best;
+  return best;
+}
+
 template <typename T, int CN>
 static int launch_warp_tile(const CUtensorMap &tmap, const WarpTileArgs &t, dim3 grid, size_t smem, cudaStream_t s) {
-  RCV_CUDA(cudaFuncSetAttribute(k_warp_tile<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_smem[16] = {};  // per instantiation, per device: largest size set so far
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_smem[dev & 15] < smem) {
+    RCV_CUDA(cudaFuncSetAttribute(k_warp_tile<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev & 15] = smem;
+  }
   k_warp_tile<T, CN><<<grid, kWarpThreads, smem, s>>>(tmap, t);
   count_launch();
   RCV_CUDA(cudaGetLastError());
@@ -493,9 +547,11 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
       t.d0 = iM[0];
       t.d3 = iM[3];
       // box width in 4-byte words: (ceil(dxw) + 4) pixels, + 15 bytes because the origin is floored to a
-      // 16-byte boundary.  16 (mod 32) words keeps the rotated gather spread over the smem banks.
-      t.bw = ((((int)ceil(dxw) + 4) * E + 15 + 3) / 4 + 15) & ~15;
-      if ((t.bw & 31) == 0) t.bw += 16;
+      // 16-byte boundary; a multiple of 4 words (TMA inner box = multiple of 16 bytes).  Among the 8
+      // residues mod 32 the one with the fewest shared-memory bank conflicts for THIS matrix is taken:
+      // a warp's 32 taps walk a line of slope (m0, m3) through the box (at 90 degrees a pitch that is a
+      // multiple of 32 words would be a 32-way conflict; at 15 degrees it is the conflict-free one).
+      t.bw = pick_box_pitch((((int)ceil(dxw) + 4) * E + 15 + 3) / 4, E, iM[0], iM[3]);
       t.bh = (int)ceil(dyh) + 4;
       const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16 + kWarpTH * 8;  // tile + mbarrier + row terms
       dim3 grid(ceil_div(a.dcols, kWarpTW), ceil_div(a.drows, kWarpTH), src.n);
