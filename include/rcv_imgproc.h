@@ -142,6 +142,11 @@ RCV_API int rcv_bgra_to_bgr_packed(const uint8_t *src, size_t src_len, uint8_t *
  * rows x cols x 1, uv is rows/2 x cols/2 x 2. */
 RCV_API int rcv_nv12_to_bgr(const RcvMat *y, const RcvMat *uv, RcvMat *dst);
 
+/* cv::Mat::convertTo between u8 and f32 Mats of one geometry (the seam between the u8 images the
+ * reference's capture path produces and the f32 images Sobel / warpAffine take):
+ * v = fmaf((float)src, (float)alpha, (float)beta); u8 results are saturate(rint(v)). */
+RCV_API int rcv_convert_to(const RcvMat *src, RcvMat *dst, double alpha, double beta);
+
 /* ---- filtering (absent from the reference; OpenCV semantics, oracle/) --- */
 /* cv::GaussianBlur, BORDER_REFLECT_101.  kw/kh odd (or 0 = derive from sigma);
  * sigma_y <= 0 means sigma_x.  u8: Q8 taps, single rounding; f32: fmaf chains. */

@@ -184,6 +184,17 @@ def bgr_to_gray(src: np.ndarray) -> np.ndarray:
     return _cvt("orc_bgr_to_gray_strided", src, (rows, cols), cols=cols)
 
 
+def convert_to(src: np.ndarray, dtype, alpha: float = 1.0, beta: float = 0.0) -> np.ndarray:
+    """cv::Mat::convertTo between u8 and f32."""
+    _check_rows(src)
+    dst = np.zeros(src.shape, dtype=dtype)
+    ncols = src.shape[1] * _cn(src)
+    lib().orc_convert_to(_p(src), _step(src), C.c_int(int(src.dtype == np.float32)), _p(dst), _step(dst),
+                         C.c_int(int(np.dtype(dtype) == np.float32)), C.c_int(src.shape[0]), C.c_int(ncols),
+                         C.c_double(alpha), C.c_double(beta))
+    return dst
+
+
 def bgr_to_xrgb32(src: np.ndarray) -> np.ndarray:
     rows, cols = src.shape[:2]
     return _cvt("orc_bgr_to_xrgb32_strided", src, (rows, cols), out_dtype=np.uint32, cols=cols)

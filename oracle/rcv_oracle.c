@@ -337,6 +337,27 @@ void orc_yuyv_to_gray_strided(const uint8_t *src, size_t sstep, uint8_t *dst,
   parallel_rows(yuyv_gray_rows, &a, rows);
 }
 
+/* cv::Mat::convertTo model: one fmaf in f32, u8 results rounded half-to-even and saturated. */
+void orc_convert_to(const void *src, size_t sstep, int sdepth, void *dst, size_t dstep, int ddepth, int rows,
+                    int ncols, double alpha, double beta) {
+  const float a = (float)alpha, b = (float)beta;
+  for (int r = 0; r < rows; ++r) {
+    const uint8_t *s8 = (const uint8_t *)src + (size_t)r * sstep;
+    const float *sf = (const float *)s8;
+    uint8_t *d8 = (uint8_t *)dst + (size_t)r * dstep;
+    float *df = (float *)d8;
+    for (int x = 0; x < ncols; ++x) {
+      float v = fmaf(sdepth ? sf[x] : (float)s8[x], a, b);
+      if (ddepth) {
+        df[x] = v;
+      } else {
+        long iv = lrintf(v);
+        d8[x] = iv < 0 ? 0 : (iv > 255 ? 255 : (uint8_t)iv);
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* Gaussian taps (OpenCV model)                                               */
 /* ------------------------------------------------------------------------ */

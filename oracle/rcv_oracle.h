@@ -70,6 +70,12 @@ void orc_bgr_to_xrgb32_strided(const uint8_t *src, size_t sstep, uint32_t *dst,
 void orc_yuyv_to_gray_strided(const uint8_t *src, size_t sstep, uint8_t *dst,
                               size_t dstep, int rows, int cols);
 
+/* cv::Mat::convertTo between u8 and f32 (depth codes 0 = u8, 1 = f32), any channel count:
+ * v = fmaf((float)src, (float)alpha, (float)beta); u8 results are saturate(rint(v)) (half to even).
+ * ncols = cols * channels. */
+void orc_convert_to(const void *src, size_t sstep, int sdepth, void *dst, size_t dstep, int ddepth, int rows,
+                    int ncols, double alpha, double beta);
+
 /* ---- filtering ---------------------------------------------------------- */
 /* OpenCV-compatible Gaussian taps.  kq sums to 256 (Q8), kd to ~1. */
 int orc_gaussian_ksize(double sigma, int is_u8);

@@ -422,6 +422,18 @@ int rcv_nv12_to_bgr(const RcvMat *y, const RcvMat *uv, RcvMat *dst) {
   return RCV_OK;
 }
 
+int rcv_convert_to(const RcvMat *src, RcvMat *dst, double alpha, double beta) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(dst, "dst"));
+  if (src->channels != dst->channels) return fail(RCV_ERR_DEPTH, "convertTo: channel counts differ");
+  if (src->data == dst->data && src->rows > 0 && src->depth != dst->depth)
+    return fail(RCV_ERR_ARG, "convertTo: in-place conversion between depths is not supported");
+  RCV_TRY(check_same_size(src, dst, "convertTo"));
+  return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_convert(c, s, d, alpha, beta, st);
+  });
+}
+
 // ---- filters -------------------------------------------------------------------------------
 int rcv_gaussian_blur(const RcvMat *src, RcvMat *dst, int32_t kw, int32_t kh, double sigma_x, double sigma_y) {
   RCV_TRY(check_filter_pair(src, dst, "GaussianBlur"));

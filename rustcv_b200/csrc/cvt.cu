@@ -361,6 +361,80 @@ int launch_cvt(Ctx *, const DBatch &src, const DBatch &dst, int code, cudaStream
   return fail(RCV_ERR_ARG, "unknown colour conversion code %d", code);
 }
 
+// ---- convertTo: u8 <-> f32 with scale/offset, 16 elements per thread ------------------------------
+struct ConvArgs {
+  const uint8_t *src;
+  size_t sstep, sfs;
+  uint8_t *dst;
+  size_t dstep, dfs;
+  int rows, ncols;  // ncols = cols * channels
+  int per_row;
+  float a, b;
+};
+
+template <typename TS, typename TD>
+__device__ __forceinline__ TD conv_one(TS v, float a, float b) {
+  const float r = fmaf((float)v, a, b);
+  if (sizeof(TD) == 1) return (TD)min(max(__float2int_rn(r), 0), 255);
+  return (TD)r;
+}
+
+template <typename TS, typename TD, bool VEC>
+__global__ void __launch_bounds__(256) k_convert(ConvArgs a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.rows * a.per_row) return;
+  const int r = (int)(t / a.per_row), g = (int)(t - (long long)r * a.per_row);
+  const TS *s = (const TS *)(a.src + (size_t)blockIdx.y * a.sfs + (size_t)r * a.sstep);
+  TD *d = (TD *)(a.dst + (size_t)blockIdx.y * a.dfs + (size_t)r * a.dstep);
+  const int x0 = g * 16;
+  if (VEC && x0 + 16 <= a.ncols) {
+    __align__(16) TS in[16];
+    __align__(16) TD out[16];
+    const uint4 *sp = (const uint4 *)(s + x0);
+#pragma unroll
+    for (int k = 0; k < (int)sizeof(TS); ++k) ((uint4 *)in)[k] = __ldg(sp + k);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) out[k] = conv_one<TS, TD>(in[k], a.a, a.b);
+    uint4 *dp = (uint4 *)(d + x0);
+#pragma unroll
+    for (int k = 0; k < (int)sizeof(TD); ++k) dp[k] = ((const uint4 *)out)[k];
+  } else {
+    for (int x = x0; x < min(x0 + 16, a.ncols); ++x) d[x] = conv_one<TS, TD>(s[x], a.a, a.b);
+  }
+}
+
+int launch_convert(Ctx *, const DBatch &src, const DBatch &dst, double alpha, double beta, cudaStream_t s) {
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "frames > 65535");
+  ConvArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows,
+             src.v.cols * src.v.cn, 0, (float)alpha, (float)beta};
+  a.per_row = ceil_div(a.ncols, 16);
+  const long long blocks = ((long long)a.rows * a.per_row + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(RCV_ERR_UNSUPPORTED, "image too large");
+  dim3 grid((unsigned)blocks, src.n, 1);
+  const bool vec = aligned16(src) && aligned16(dst);
+  const bool sf = src.v.depth == RCV_F32, df = dst.v.depth == RCV_F32;
+#define RCV_CONV(TS, TD)                                         \
+  do {                                                           \
+    if (vec)                                                     \
+      k_convert<TS, TD, true><<<grid, 256, 0, s>>>(a);           \
+    else                                                         \
+      k_convert<TS, TD, false><<<grid, 256, 0, s>>>(a);          \
+  } while (0)
+  if (!sf && df)
+    RCV_CONV(uint8_t, float);
+  else if (sf && !df)
+    RCV_CONV(float, uint8_t);
+  else if (sf && df)
+    RCV_CONV(float, float);
+  else
+    RCV_CONV(uint8_t, uint8_t);
+#undef RCV_CONV
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
 int launch_nv12(Ctx *, const DView &y, const DView &uv, const DView &dst, cudaStream_t s) {
   if (y.rows > 65535) return fail(RCV_ERR_UNSUPPORTED, "rows > 65535");
   if (y.rows == 0 || y.cols == 0) return RCV_OK;

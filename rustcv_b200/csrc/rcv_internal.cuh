@@ -106,6 +106,7 @@ int make_tmap_rows_u32(CUtensorMap *out, const void *base, size_t row_bytes, int
 // ---- kernel launchers (device views only; enqueue on `s`) ------------------------
 int launch_cvt(Ctx *c, const DBatch &src, const DBatch &dst, int code, cudaStream_t s);
 int launch_nv12(Ctx *c, const DView &y, const DView &uv, const DView &dst, cudaStream_t s);
+int launch_convert(Ctx *c, const DBatch &src, const DBatch &dst, double alpha, double beta, cudaStream_t s);
 
 int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh, double sx, double sy,
                     cudaStream_t s);

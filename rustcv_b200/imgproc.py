@@ -60,6 +60,12 @@ def nv12_to_bgr(y: Mat, uv: Mat, dst: Mat) -> None:
     F.check(F.lib.rcv_nv12_to_bgr(C.byref(y.c()), C.byref(uv.c()), C.byref(dst.c())))
 
 
+def convert_to(src: Mat, dst: Mat, depth: int, alpha: float = 1.0, beta: float = 0.0) -> None:
+    """cv::Mat::convertTo between u8 and f32 (dst = saturate(src*alpha + beta))."""
+    _size_dst(dst, src.rows, src.cols, src.channels, depth)
+    F.check(F.lib.rcv_convert_to(C.byref(src.c()), C.byref(dst.c()), alpha, beta))
+
+
 def gaussian_blur(src: Mat, dst: Mat, ksize=(5, 5), sigma_x: float = 0.0, sigma_y: float = 0.0) -> None:
     _size_dst(dst, src.rows, src.cols, src.channels, src.depth)
     F.check(F.lib.rcv_gaussian_blur(C.byref(src.c()), C.byref(dst.c()), ksize[0], ksize[1], sigma_x, sigma_y))

@@ -66,6 +66,8 @@ extern "C" {
     pub fn rcv_bgra_to_bgr_packed(src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, width: usize, height: usize) -> c_int;
     pub fn rcv_nv12_to_bgr(y: *const RcvMat, uv: *const RcvMat, dst: *mut RcvMat) -> c_int;
 
+    pub fn rcv_convert_to(src: *const RcvMat, dst: *mut RcvMat, alpha: f64, beta: f64) -> c_int;
+
     pub fn rcv_gaussian_blur(src: *const RcvMat, dst: *mut RcvMat, kw: i32, kh: i32, sigma_x: f64, sigma_y: f64) -> c_int;
     pub fn rcv_sep_filter2d(src: *const RcvMat, dst: *mut RcvMat, kx: *const f32, kw: i32, ky: *const f32, kh: i32) -> c_int;
     pub fn rcv_sep_filter2d_q8(src: *const RcvMat, dst: *mut RcvMat, kx: *const i32, kw: i32, ky: *const i32, kh: i32) -> c_int;

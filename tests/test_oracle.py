@@ -217,3 +217,18 @@ def test_strided_inputs_equal_packed(oracle):
     assert (oracle.gaussian_blur(p, (5, 5)) == oracle.gaussian_blur(img, (5, 5))).all()
     assert (oracle.bgr_to_gray(p) == oracle.bgr_to_gray(img)).all()
     assert (oracle.resize_bilinear(p, 20, 31) == oracle.resize_bilinear(img, 20, 31)).all()
+
+
+def test_convert_to_model(oracle):
+    rng = np.random.default_rng(3)
+    u = rng.integers(0, 256, size=(17, 29, 3), dtype=np.uint8)
+    f = oracle.convert_to(u, np.float32, 1.0 / 255.0, 0.0)
+    assert f.dtype == np.float32 and (f == (u.astype(np.float32) * np.float32(1.0 / 255.0))).all()
+    back = oracle.convert_to(f, np.uint8, 255.0, 0.0)
+    assert (back == u).all()
+    # half-to-even rounding and saturation
+    v = np.array([[0.5, 1.5, 2.5, -3.0, 254.5, 255.5, 300.0, np.float32(1e9)]], np.float32)
+    assert oracle.convert_to(v, np.uint8).ravel().tolist() == [0, 2, 2, 0, 254, 255, 255, 255]
+    cv2 = pytest.importorskip("cv2")
+    assert np.abs(cv2.convertScaleAbs(v) .astype(int) - oracle.convert_to(np.abs(v), np.uint8).astype(int)).max() <= 1
+    assert (oracle.convert_to(u, np.float32) == u.astype(np.float32)).all()

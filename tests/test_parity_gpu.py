@@ -910,3 +910,32 @@ def test_decode_frame_into_device_mat_then_process(rcv, oracle):
     bgr = oracle.fill_u8(9, w * h * 3)
     assert R.videoio.decode_frame(bgr, w, h, R.videoio.BGR3, frame)
     assert (frame.to_numpy().ravel() == bgr).all()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_convert_to_and_gray_sobel_chain(rcv, oracle, where):
+    """u8 <-> f32 conversion, and the capture-side chain BGR -> Gray -> f32 -> Sobel magnitude on one GPU."""
+    R = rcv
+    rng = np.random.default_rng(11)
+    for shape in ((61, 83, 3), (40, 333), (5, 7, 4)):
+        u = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        s = mats(R, u, where)
+        d = out_like(R, s, where, depth=R.F32)
+        R.imgproc.convert_to(s, d, R.F32, 1.0 / 255.0, 0.25)
+        want = oracle.convert_to(u, np.float32, 1.0 / 255.0, 0.25)
+        assert_f32(d.to_numpy().reshape(shape[0], -1), want.reshape(shape[0], -1), f"u8->f32 {shape}", max_ulp=0)
+        f = (rng.random(size=shape, dtype=np.float32) * 300 - 20).astype(np.float32)
+        s = mats(R, f, where)
+        d = out_like(R, s, where, depth=R.U8)
+        R.imgproc.convert_to(s, d, R.U8, 0.9, 3.5)
+        assert_same(d.to_numpy(), oracle.convert_to(f, np.uint8, 0.9, 3.5), f"f32->u8 {shape}")
+    bgr = oracle.fill_u8(210, 270 * 480 * 3).reshape(270, 480, 3)
+    s = mats(R, bgr, where)
+    g = out_like(R, s, where, channels=1)
+    R.imgproc.cvt_color(s, g, R.imgproc.COLOR_BGR2GRAY)
+    gf = out_like(R, g, where, depth=R.F32)
+    R.imgproc.convert_to(g, gf, R.F32, 1.0 / 255.0)
+    m = out_like(R, gf, where)
+    R.imgproc.sobel_mag(gf, m)
+    want = oracle.sobel3(oracle.convert_to(oracle.bgr_to_gray(bgr), np.float32, 1.0 / 255.0))["mag"]
+    assert_f32(m.to_numpy(), want, f"gray->f32->sobel {where}", max_ulp=1)
