@@ -174,6 +174,11 @@ RCV_API int rcv_invert_affine(const double M[6], double iM[6]);
 /* ---- fused chains (the step upstream of every imgproc call) ------------- */
 /* GaussianBlur5x5(YUYV2BGR(src)) without the intermediate BGR round trip. */
 RCV_API int rcv_yuyv_to_bgr_gaussian5(const RcvMat *src_yuyv, RcvMat *dst_bgr);
+/* SobelMagnitude(convertTo_f32(BGR2GRAY(YUYV2BGR(src)))) in ONE kernel: the raw
+ * camera frame (rustcv/src/videoio/mod.rs:201-205, channels=2, even cols) in,
+ * the f32 gradient magnitude (channels=1, same rows x cols) out -- 6 B/px of
+ * HBM traffic instead of the chain's 22.  Bit-identical to the chain. */
+RCV_API int rcv_yuyv_to_sobel_mag(const RcvMat *src_yuyv, RcvMat *mag_f32);
 
 /* ---- batches of independent frames -------------------------------------
  * srcs[i] -> dsts[i], i < n, all of one geometry and location.  Device Mats:
@@ -186,6 +191,7 @@ RCV_API int rcv_resize_bilinear_batch(const RcvMat *srcs, RcvMat *dsts, int32_t 
 RCV_API int rcv_warp_affine_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const double M[6],
                           int32_t inverse_map, double border_value);
 RCV_API int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code);
+RCV_API int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs_yuyv, RcvMat *mags_f32, int32_t n);
 
 /* ---- tuning knobs (benchmark/diagnostic use) ----------------------------- */
 /* name/value integer options, e.g. "gauss.band_rows", "gauss.variant". */

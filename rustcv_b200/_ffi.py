@@ -82,6 +82,8 @@ SIGNATURES = {
     "rcv_get_rotation_matrix_2d": [C.c_double, C.c_double, C.c_double, C.c_double, _P(C.c_double)],
     "rcv_invert_affine": [_P(C.c_double), _P(C.c_double)],
     "rcv_yuyv_to_bgr_gaussian5": [_MatP, _MatP],
+    "rcv_yuyv_to_sobel_mag": [_MatP, _MatP],
+    "rcv_yuyv_to_sobel_mag_batch": [_MatP, _MatP, C.c_int32],
     "rcv_gaussian_blur_batch": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double],
     "rcv_sobel_mag_batch": [_MatP, _MatP, C.c_int32],
     "rcv_resize_bilinear_batch": [_MatP, _MatP, C.c_int32],

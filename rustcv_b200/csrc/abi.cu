@@ -619,4 +619,31 @@ int rcv_yuyv_to_bgr_gaussian5(const RcvMat *src, RcvMat *dst) {
   });
 }
 
+static int check_yuyv_sobel(const RcvMat *src, const RcvMat *mag) {
+  RCV_TRY(check_mat(src, "src"));
+  RCV_TRY(check_mat(mag, "mag"));
+  if (src->depth != RCV_U8 || src->channels != 2) return fail(RCV_ERR_DEPTH, "YUYV source must be u8 with channels = 2");
+  if (mag->depth != RCV_F32 || mag->channels != 1) return fail(RCV_ERR_DEPTH, "magnitude must be f32 with channels = 1");
+  if (src->cols & 1) return fail(RCV_ERR_SIZE, "YUYV width %d is odd", src->cols);
+  return check_same_size(src, mag, "YUYV->Sobel");
+}
+
+int rcv_yuyv_to_sobel_mag(const RcvMat *src, RcvMat *mag) {
+  RCV_TRY(check_yuyv_sobel(src, mag));
+  return run_unary(src, mag, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_yuyv_sobel(c, s, d, st);
+  });
+}
+
+int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
+  if (n < 0 || (n > 0 && (!srcs || !mags))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(mags, n, "mags"));
+  RCV_TRY(check_yuyv_sobel(&srcs[0], &mags[0]));
+  return run_batch(srcs, mags, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_yuyv_sobel(c, s, d, st);
+  });
+}
+
 }  // extern "C"

@@ -1,0 +1,45 @@
+// cvt_math.cuh -- per-pixel conversion arithmetic shared by cvt.cu and the fused strip ops.
+#pragma once
+
+#include <stdint.h>
+
+namespace rcv {
+
+// OpenCV 4.13 BGR2GRAY (15-bit coefficients), bit-exact with cv2.cvtColor.
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
+  return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+}
+
+// ---- BT.601 for the vector kernel ----------------------------------------------------------
+// The reference formula (videoio/mod.rs:352-369) per channel is clamp((298*c + k1*u + k2*v + 128) >> 8)
+// with c = y-16, u = U-128, v = V-128.  Folding the offsets into one constant per channel gives
+//   B = 298*y + 516*U - 70688      G = 298*y - 100*U - 208*V + 34784      R = 298*y + 409*V - 56992
+// (all exact in i32): 2 IMAD for the luma terms, 4 for the chroma terms shared by both pixels,
+// 6 adds.  clamp(x >> 8) equals byte 1 of min(max(x, 0), 65535) (x < 0 -> 0; x >= 65536 -> 0xFFFF
+// -> 255; else floor(x / 256)), so shift + clamp is ONE VIMNMX.RELU (__vimin_s32_relu) and the
+// result bytes are gathered with PRMT (dp2a / cvt.pack are emulated on sm_100a -- measured slower).
+struct Px6 {
+  uint32_t b0, g0, r0, b1, g1, r1;  // clamped to [0, 65535]; the channel value is byte 1
+};
+
+template <bool UYVY>
+__device__ __forceinline__ Px6 yuv_word(uint32_t w) {
+  const int y0 = (int)__byte_perm(w, 0, UYVY ? 0x4441 : 0x4440);
+  const int u = (int)__byte_perm(w, 0, UYVY ? 0x4440 : 0x4441);
+  const int y1 = (int)__byte_perm(w, 0, UYVY ? 0x4443 : 0x4442);
+  const int v = (int)__byte_perm(w, 0, UYVY ? 0x4442 : 0x4443);
+  const int cy0 = y0 * 298, cy1 = y1 * 298;
+  const int db = u * 516 - 70688;
+  const int dr = v * 409 - 56992;
+  const int dg = u * -100 + (v * -208 + 34784);
+  Px6 o;
+  o.b0 = (uint32_t)__vimin_s32_relu(cy0 + db, 65535);
+  o.g0 = (uint32_t)__vimin_s32_relu(cy0 + dg, 65535);
+  o.r0 = (uint32_t)__vimin_s32_relu(cy0 + dr, 65535);
+  o.b1 = (uint32_t)__vimin_s32_relu(cy1 + db, 65535);
+  o.g1 = (uint32_t)__vimin_s32_relu(cy1 + dg, 65535);
+  o.r1 = (uint32_t)__vimin_s32_relu(cy1 + dr, 65535);
+  return o;
+}
+
+}  // namespace rcv

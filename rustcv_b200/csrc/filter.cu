@@ -8,6 +8,8 @@
 // orc_sobel3_f32 in oracle/rcv_oracle.c.
 #include "rcv_internal.cuh"
 
+#include <cstring>
+
 #include <cmath>
 
 namespace rcv {
@@ -284,6 +286,36 @@ int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_
   RCV_TRY(launch_cvt(c, src, tmp, RCV_COLOR_YUYV2BGR, s));
   // an odd trailing column is left untouched by the conversion (cols/2 macro-pixels per row)
   return launch_gaussian(c, tmp, dst, 5, 5, 0.0, 0.0, s);
+}
+
+// YUYV -> BGR -> Gray -> f32 -> Sobel magnitude.  One fused strip kernel (strip_yuyv_sobel.cu) whenever the
+// strip path applies; tiny or unaligned images run the chain's stand-alone kernels over device scratch.
+int launch_yuyv_sobel_strip(Ctx *c, const DBatch &src, const DBatch &mag, cudaStream_t s);
+
+int launch_yuyv_sobel(Ctx *c, const DBatch &src, const DBatch &mag, cudaStream_t s) {
+  if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (opt_get("yuyvsobel.force_chain", 0) == 0) {
+    int rc = launch_yuyv_sobel_strip(c, src, mag, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
+  DBatch g8 = mag, g32 = mag;
+  const size_t p8 = ((size_t)src.v.cols + 255) / 256 * 256, p32 = ((size_t)src.v.cols * 4 + 255) / 256 * 256;
+  void *a = nullptr, *b = nullptr;
+  RCV_TRY(ctx_scratch(c, SCR_FUSE_TMP, p8 * src.v.rows * src.n, &a));
+  RCV_TRY(ctx_scratch(c, SCR_FUSE_TMP2, p32 * src.v.rows * src.n, &b));
+  g8.v.data = (uint8_t *)a;
+  g8.v.step = p8;
+  g8.v.depth = RCV_U8;
+  g8.frame_stride = src.n > 1 ? p8 * src.v.rows : 0;
+  g32.v.data = (uint8_t *)b;
+  g32.v.step = p32;
+  g32.frame_stride = src.n > 1 ? p32 * src.v.rows : 0;
+  RCV_TRY(launch_cvt(c, src, g8, RCV_COLOR_YUYV2GRAY, s));
+  RCV_TRY(launch_convert(c, g8, g32, 1.0, 0.0, s));
+  DBatch none;
+  memset(&none, 0, sizeof(none));
+  none.n = src.n;
+  return launch_sobel(c, g32, mag, none, none, s);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_warp_affine(const WarpArgs a) {
 // memory instead of from L1/L2 (a rotated warp row touches ~9 cache lines per tap in global
 // memory: the direct kernel is L1-wavefront bound, 5x off the HBM roofline).  Arithmetic and
 // the in-image tests are exactly those of k_warp_affine / the oracle.
-constexpr int kWarpTW = 64, kWarpTH = 32, kWarpThreads = 256;
+constexpr int kWarpTW = 64, kWarpThreads = 256;  // tile height TH = 32 or 64 rows (template parameter)
 
 struct WarpTileArgs {
   WarpArgs a;
@@ -365,7 +365,7 @@ __device__ __forceinline__ void warp_pixel(const WarpTileArgs &t, uint32_t tile,
   }
 }
 
-template <typename T, int CN>
+template <typename T, int CN, int TH>
 __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constant__ CUtensorMap tmap,
                                                             const WarpTileArgs t) {
   // no static shared memory in this kernel: the TMA destination must be 128-byte aligned and the
@@ -374,13 +374,13 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
   constexpr int E = CN * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const WarpArgs &a = t.a;
-  const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * kWarpTH;
+  const int tx0 = blockIdx.x * kWarpTW, ty0 = blockIdx.y * TH;
   const uint32_t tile = smem_u32(smem_raw);
   const uint32_t barp = tile + (((uint32_t)(t.bw * t.bh * 4) + 15u) & ~15u);
   const uint32_t rowtab = barp + 16;
   if (threadIdx.x == 0) {
     // bounding box origin from the four tile corners (f64), once per tile
-    const double xs[2] = {(double)tx0, (double)(tx0 + kWarpTW - 1)}, ys[2] = {(double)ty0, (double)(ty0 + kWarpTH - 1)};
+    const double xs[2] = {(double)tx0, (double)(tx0 + kWarpTW - 1)}, ys[2] = {(double)ty0, (double)(ty0 + TH - 1)};
     double minx = 1e300, miny = 1e300;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
     mbar_expect_tx(barp, (uint32_t)(t.bw * t.bh * 4));
     tma_load_3d(tile, &tmap, barp, ox >> 2, oy, (int)blockIdx.z);
   }
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + kWarpTH) {
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + TH) {
     // row terms, once per tile row: bx = (float)(iM[1]*y + iM[2]) -- f64 mul, f64 add, one rounding
     const int r = threadIdx.x - 32;
     const double y = (double)(ty0 + r);
@@ -420,11 +420,11 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   uint8_t *drow = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)(ty0 + ly0) * a.dstep + (size_t)x * E;
   const bool interior = bx0 >= 0 && by0 >= 0 && bx0 + t.bw * 4 <= a.scols * E && by0 + t.bh <= a.srows;
-  const bool full = tx0 + kWarpTW <= a.dcols && ty0 + kWarpTH <= a.drows;
+  const bool full = tx0 + kWarpTW <= a.dcols && ty0 + TH <= a.drows;
   mbar_wait(barp, 0);
   if (interior && full) {
 #pragma unroll
-    for (int k = 0; k < kWarpTH / 4; ++k) {
+    for (int k = 0; k < TH / 4; ++k) {
       float bx, by;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
       T v[CN];
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
     }
   } else {
 #pragma unroll 2
-    for (int k = 0; k < kWarpTH / 4; ++k) {
+    for (int k = 0; k < TH / 4; ++k) {
       const int y = ty0 + ly0 + 4 * k;
       float bx, by;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
@@ -495,19 +495,54 @@ static int pick_box_pitch(int min_words, int E, double m0, double m3) {
   return best;
 }
 
-template <typename T, int CN>
+template <typename T, int CN, int TH>
 static int launch_warp_tile(const CUtensorMap &tmap, const WarpTileArgs &t, dim3 grid, size_t smem, cudaStream_t s) {
   static size_t attr_smem[16] = {};  // per instantiation, per device: largest size set so far
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_smem[dev & 15] < smem) {
-    RCV_CUDA(cudaFuncSetAttribute(k_warp_tile<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RCV_CUDA(cudaFuncSetAttribute(k_warp_tile<T, CN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[dev & 15] = smem;
   }
-  k_warp_tile<T, CN><<<grid, kWarpThreads, smem, s>>>(tmap, t);
+  k_warp_tile<T, CN, TH><<<grid, kWarpThreads, smem, s>>>(tmap, t);
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;
+}
+
+// Tries the TMA-staged kernel with TH-row tiles.  Returns RCV_ERR_UNSUPPORTED (without setting the error
+// string) when the tile's bounding box does not fit: the caller then tries the next shape.
+template <int TH>
+static int try_warp_tile(const DBatch &src, const WarpArgs &a, const double iM[6], size_t smem_cap, cudaStream_t s) {
+  const int E = (int)src.v.elem() * src.v.cn;  // bytes per pixel
+  const double dxw = fabs(iM[0]) * (kWarpTW - 1) + fabs(iM[1]) * (TH - 1);
+  const double dyh = fabs(iM[3]) * (kWarpTW - 1) + fabs(iM[4]) * (TH - 1);
+  if (!(dxw < 250.0 && dyh < 250.0)) return RCV_ERR_UNSUPPORTED;
+  WarpTileArgs t;
+  t.a = a;
+  t.d0 = iM[0];
+  t.d3 = iM[3];
+  // box width in 4-byte words: (ceil(dxw) + 4) pixels, + 15 bytes because the origin is floored to a
+  // 16-byte boundary; a multiple of 4 words (TMA inner box = multiple of 16 bytes).  Among the 8
+  // residues mod 32 the one with the fewest shared-memory bank conflicts for THIS matrix is taken:
+  // a warp's 32 taps walk a line of slope (m0, m3) through the box (at 90 degrees a pitch that is a
+  // multiple of 32 words would be a 32-way conflict; at 15 degrees it is the conflict-free one).
+  t.bw = pick_box_pitch((((int)ceil(dxw) + 4) * E + 15 + 3) / 4, E, iM[0], iM[3]);
+  t.bh = (int)ceil(dyh) + 4;
+  const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16 + TH * 8;  // tile + mbarrier + row terms
+  dim3 grid(ceil_div(a.dcols, kWarpTW), ceil_div(a.drows, TH), src.n);
+  if (!(t.bw <= 256 && t.bh <= 256 && smem <= smem_cap && grid.y <= 65535)) return RCV_ERR_UNSUPPORTED;
+  CUtensorMap tmap;
+  RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
+                             t.bw, t.bh));
+  if (src.v.depth == RCV_F32) return launch_warp_tile<float, 1, TH>(tmap, t, grid, smem, s);
+  switch (src.v.cn) {
+    case 1: return launch_warp_tile<uint8_t, 1, TH>(tmap, t, grid, smem, s);
+    case 2: return launch_warp_tile<uint8_t, 2, TH>(tmap, t, grid, smem, s);
+    case 3: return launch_warp_tile<uint8_t, 3, TH>(tmap, t, grid, smem, s);
+    case 4: return launch_warp_tile<uint8_t, 4, TH>(tmap, t, grid, smem, s);
+  }
+  return RCV_ERR_UNSUPPORTED;
 }
 
 int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const double iM[6], double border,
@@ -534,40 +569,20 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
   a.m5 = iM[5];
   a.border = src.v.depth == RCV_U8 ? (float)(int)border : (float)border;
 
-  // TMA-staged path: f32 C1 or u8 C1..C4, 16-byte aligned source, bounding box small enough for smem
+  // TMA-staged path: f32 C1 or u8 C1..C4, 16-byte aligned source, bounding box small enough for smem.
+  // 64x64 (else 64x48) tiles when the box stays under 36 KB: the per-tile prologue -- corner arithmetic in
+  // f64, barrier set-up, row terms, ~100 instructions per thread -- is amortised over 16 (12) pixels per
+  // thread instead of 8, and the box over-read shrinks (15 degrees: 1.7x vs 2.0x); else 64x32 tiles up to 96 KB.
   const bool tile_type = (src.v.depth == RCV_F32 && src.v.cn == 1) || src.v.depth == RCV_U8;
   if (tile_type && src.v.rows > 0 && src.v.cols > 0 &&
       ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 15) == 0) && opt_get("warp.force_generic", 0) == 0) {
-    const int E = (int)src.v.elem() * src.v.cn;  // bytes per pixel
-    const double dxw = fabs(iM[0]) * (kWarpTW - 1) + fabs(iM[1]) * (kWarpTH - 1);
-    const double dyh = fabs(iM[3]) * (kWarpTW - 1) + fabs(iM[4]) * (kWarpTH - 1);
-    if (dxw < 250.0 && dyh < 250.0) {
-      WarpTileArgs t;
-      t.a = a;
-      t.d0 = iM[0];
-      t.d3 = iM[3];
-      // box width in 4-byte words: (ceil(dxw) + 4) pixels, + 15 bytes because the origin is floored to a
-      // 16-byte boundary; a multiple of 4 words (TMA inner box = multiple of 16 bytes).  Among the 8
-      // residues mod 32 the one with the fewest shared-memory bank conflicts for THIS matrix is taken:
-      // a warp's 32 taps walk a line of slope (m0, m3) through the box (at 90 degrees a pitch that is a
-      // multiple of 32 words would be a 32-way conflict; at 15 degrees it is the conflict-free one).
-      t.bw = pick_box_pitch((((int)ceil(dxw) + 4) * E + 15 + 3) / 4, E, iM[0], iM[3]);
-      t.bh = (int)ceil(dyh) + 4;
-      const size_t smem = (((size_t)t.bw * t.bh * 4 + 15) & ~(size_t)15) + 16 + kWarpTH * 8;  // tile + mbarrier + row terms
-      dim3 grid(ceil_div(a.dcols, kWarpTW), ceil_div(a.drows, kWarpTH), src.n);
-      if (t.bw <= 256 && t.bh <= 256 && smem <= 96 * 1024 && grid.y <= 65535) {
-        CUtensorMap tmap;
-        RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n,
-                                   src.frame_stride, t.bw, t.bh));
-        if (src.v.depth == RCV_F32) return launch_warp_tile<float, 1>(tmap, t, grid, smem, s);
-        switch (src.v.cn) {
-          case 1: return launch_warp_tile<uint8_t, 1>(tmap, t, grid, smem, s);
-          case 2: return launch_warp_tile<uint8_t, 2>(tmap, t, grid, smem, s);
-          case 3: return launch_warp_tile<uint8_t, 3>(tmap, t, grid, smem, s);
-          case 4: return launch_warp_tile<uint8_t, 4>(tmap, t, grid, smem, s);
-        }
-      }
-    }
+    int rc = RCV_ERR_UNSUPPORTED;
+    const int64_t th = opt_get("warp.tile_rows", 0);  // 0 = automatic; 32 / 48 / 64 force one shape
+    const size_t big = 96 * 1024, cap = 36 * 1024;    // 36 KB boxes: 6 CTAs (48 warps) per SM
+    if ((th == 0 && a.drows >= 64) || th == 64) rc = try_warp_tile<64>(src, a, iM, th ? big : cap, s);
+    if (rc == RCV_ERR_UNSUPPORTED && ((th == 0 && a.drows >= 48) || th == 48)) rc = try_warp_tile<48>(src, a, iM, th ? big : cap, s);
+    if (rc == RCV_ERR_UNSUPPORTED) rc = try_warp_tile<32>(src, a, iM, big, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
 
   dim3 block(32, 8, 1);

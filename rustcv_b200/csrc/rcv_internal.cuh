@@ -4,7 +4,7 @@
 //   context.cu   per-GPU context, streams, staging rings, device Mats, options
 //   tma.cu       cuTensorMapEncodeTiled plumbing (driver entry point, no -lcuda)
 //   cvt.cu       pixel-format conversion kernels     (videoio/mod.rs:344-399)
-//   strip_*.cu   TMA strip-pipeline kernels (strip_pipeline.cuh): Gaussian u8, Sobel f32
+//   strip_*.cu   TMA strip-pipeline kernels (strip_pipeline.cuh): Gaussian u8, Sobel f32, filters, fused YUYV->Sobel
 //   filter.cu    generic separable / dense filters (u8 Q8, f32)
 //   geom.cu      bilinear resize, warpAffine
 //   abi.cu       the extern "C" entry points of include/rcv_imgproc.h
@@ -67,7 +67,8 @@ enum ScratchSlot {
   SCR_TABLE_Y = 25,
   SCR_TAPS = 26,
   SCR_COUNTER = 28,   // work-stealing counter of the strip kernels
-  SCR_FUSE_TMP = 27,  // intermediate BGR of the two-pass YUYV->BGR->Gaussian chain
+  SCR_FUSE_TMP = 27,  // intermediate BGR of the two-pass YUYV->BGR->Gaussian chain (gray u8 of the Sobel chain's backstop)
+  SCR_FUSE_TMP2 = 29, // gray f32 of the unfused YUYV->Sobel backstop
   SCR_COUNT = 32
 };
 
@@ -123,6 +124,7 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
 int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const double iM[6], double border,
                        cudaStream_t s);
 int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_yuyv_sobel(Ctx *c, const DBatch &src, const DBatch &mag, cudaStream_t s);
 
 // host-side helpers shared by abi.cu and the launchers (OpenCV models, see oracle/)
 int gaussian_ksize(double sigma, bool is_u8);

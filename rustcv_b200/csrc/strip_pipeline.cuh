@@ -28,6 +28,8 @@
 #include "rcv_internal.cuh"
 #include "tma_ptx.cuh"
 
+#include <type_traits>
+
 namespace rcv {
 
 // ---------------------------------------------------------------------------------------
@@ -56,6 +58,20 @@ struct StripParams {
   float ftaps[52];                // SepF32Op: kx[0..KS) then ky[0..KS); Filter2dOp: KS*KS taps row-major, then delta
 };
 
+// Optional op traits (absent = 1 / 0):
+//   Op::OMUL  output bytes per input byte: a lane that owns 16 input bytes writes 16*OMUL output bytes
+//             (the fused YUYV -> Sobel op turns 8 pixels of 2 bytes into 8 floats);
+//   Op::MACRO horizontal border elements are macro-pixels reflected INCLUDING the edge element
+//             (element -1 <- element 0, element n <- element n-1) instead of REFLECT_101.
+template <class Op, class = void>
+struct OpOmul { static constexpr int value = 1; };
+template <class Op>
+struct OpOmul<Op, std::void_t<decltype(Op::OMUL)>> { static constexpr int value = Op::OMUL; };
+template <class Op, class = void>
+struct OpMacro { static constexpr int value = 0; };
+template <class Op>
+struct OpMacro<Op, std::void_t<decltype(Op::MACRO)>> { static constexpr int value = Op::MACRO; };
+
 // ---------------------------------------------------------------------------------------
 // the strip pipeline
 // ---------------------------------------------------------------------------------------
@@ -64,6 +80,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   static_assert(R == 8 && R >= 2 * Op::HV + 1, "chunk rows (the ops' window rotation assumes 8-row chunks)");
   static_assert(Op::E * (Op::P + 1) <= 16, "horizontal halo must fit the 16-byte halo lanes");
   constexpr int HV = Op::HV, P = Op::P, E = Op::E;
+  constexpr int OM = OpOmul<Op>::value, RO = OpMacro<Op>::value;
   constexpr uint32_t kStageBytes = R * kTileBytes;
   extern __shared__ __align__(128) uint8_t smem_raw[];
 
@@ -113,13 +130,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     // this lane's slice of the outputs
     const int xl = x0 + (lane - 1) * kLaneBytes;
     int nvalid = 0;
-    if (lane >= 1 && lane <= 30) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes);
+    if (lane >= 1 && lane <= 30) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes) * OM;  // in OUTPUT bytes
     // output pointers of the next row to emit (row y0), advanced by one step per emitted row
     uint8_t *optr[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       optr[k] = (k < Op::NOUT && p.out[k].data)
-                    ? p.out[k].data + (size_t)frame * p.out[k].fs + (size_t)y0 * p.out[k].step + xl
+                    ? p.out[k].data + (size_t)frame * p.out[k].fs + (size_t)y0 * p.out[k].step + (long long)xl * OM
                     : nullptr;
 
     auto issue = [&](int c) {
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
 #pragma unroll
             for (int k = 1; k <= P; ++k)
 #pragma unroll
-              for (int b = 0; b < E; ++b) sts8(row + kLaneBytes - k * E + b, lds8(row + kLaneBytes + k * E + b));
+              for (int b = 0; b < E; ++b) sts8(row + kLaneBytes - k * E + b, lds8(row + kLaneBytes + (k - RO) * E + b));
           }
           if (right_edge) {
 #pragma unroll
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
 #pragma unroll
               for (int b = 0; b < E; ++b) {
                 const int dsto = xr + (k - 1) * E + b;
-                if (dsto < kTileBytes) sts8(row + dsto, lds8(row + xr - (k + 1) * E + b));
+                if (dsto < kTileBytes) sts8(row + dsto, lds8(row + xr - (k + 1 - RO) * E + b));
               }
           }
         }

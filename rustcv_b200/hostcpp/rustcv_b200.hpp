@@ -192,6 +192,14 @@ inline Result sobel_magnitude(const Mat &src, Mat &mag) {
   return check(rcv_sobel_mag(&s, &d, nullptr, nullptr));
 }
 
+// Fused decode -> process chain: the raw YUYV frame (channels = 2) -> BGR -> Gray -> f32 -> Sobel magnitude in
+// one kernel; bit-identical to cvt_color x2 + convert_to + sobel_magnitude.
+inline Result yuyv_to_sobel_magnitude(const Mat &src_yuyv, Mat &mag) {
+  mag.ensure_size(src_yuyv.rows, src_yuyv.cols, 1, core::F32);
+  RcvMat s = src_yuyv.pod(), d = mag.pod();
+  return check(rcv_yuyv_to_sobel_mag(&s, &d));
+}
+
 inline Result resize(const Mat &src, Mat &dst, Size dsize) {
   dst.ensure_size(dsize.height, dsize.width, src.channels, src.depth);
   RcvMat s = src.pod(), d = dst.pod();

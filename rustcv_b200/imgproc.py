@@ -132,6 +132,12 @@ def yuyv_to_bgr_gaussian5(src: Mat, dst: Mat) -> None:
     F.check(F.lib.rcv_yuyv_to_bgr_gaussian5(C.byref(src.c()), C.byref(dst.c())))
 
 
+def yuyv_to_sobel_mag(src: Mat, mag: Mat) -> None:
+    """sobel_mag(convert_to(cvt_color(cvt_color(src, YUYV2BGR), BGR2GRAY), F32)) in one kernel (bit-identical)."""
+    _size_dst(mag, src.rows, src.cols, 1, F32)
+    F.check(F.lib.rcv_yuyv_to_sobel_mag(C.byref(src.c()), C.byref(mag.c())))
+
+
 # ---- batches of independent frames -------------------------------------------------------
 def _arr(b) -> tuple:
     if isinstance(b, MatBatch):
@@ -174,6 +180,13 @@ def cvt_color_batch(srcs, dsts, code: int) -> None:
     da, m = _arr(dsts)
     assert n == m
     F.check(F.lib.rcv_cvt_color_batch(sa, da, n, code))
+
+
+def yuyv_to_sobel_mag_batch(srcs, mags) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(mags)
+    assert n == m
+    F.check(F.lib.rcv_yuyv_to_sobel_mag_batch(sa, da, n))
 
 
 # ---- runtime knobs ---------------------------------------------------------------------------

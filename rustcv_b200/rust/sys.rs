@@ -77,6 +77,10 @@ extern "C" {
     pub fn rcv_warp_affine(src: *const RcvMat, dst: *mut RcvMat, m: *const f64, inverse_map: i32, border_value: f64) -> c_int;
     pub fn rcv_get_rotation_matrix_2d(cx: f64, cy: f64, angle_deg: f64, scale: f64, m: *mut f64) -> c_int;
 
+    pub fn rcv_yuyv_to_bgr_gaussian5(src_yuyv: *const RcvMat, dst_bgr: *mut RcvMat) -> c_int;
+    pub fn rcv_yuyv_to_sobel_mag(src_yuyv: *const RcvMat, mag_f32: *mut RcvMat) -> c_int;
+    pub fn rcv_yuyv_to_sobel_mag_batch(srcs_yuyv: *const RcvMat, mags_f32: *mut RcvMat, n: i32) -> c_int;
+
     pub fn rcv_gaussian_blur_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, kw: i32, kh: i32, sigma_x: f64, sigma_y: f64) -> c_int;
     pub fn rcv_resize_bilinear_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32) -> c_int;
     pub fn rcv_warp_affine_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, m: *const f64, inverse_map: i32, border_value: f64) -> c_int;

@@ -163,7 +163,63 @@ def cfg5(n=8):
     src.free(); dst.free()
 
 
-ALL = {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
+def chain(n=32):
+    """raw 1080p YUYV frame -> Sobel magnitude.  The fused kernel (6 B/px) against the
+    library's own chain of stand-alone kernels (YUYV2GRAY 3 B/px, convertTo 5, Sobel 8: 16 B/px; with the BGR
+    intermediate a user of the separate calls would make it is 22)."""
+    h, w = 1080, 1920
+    src, dst = R.Mat.device_batch(n, h, w, 2), R.Mat.device_batch(n, h, w, 1, R.F32)
+    base = O.fill_u8(6, h * w * 2)
+    fill_batch(src, lambda i: np.roll(base, i * 31).reshape(h, w, 2))
+    ms = timeit(lambda: R.imgproc.yuyv_to_sobel_mag_batch(src, dst))
+    O.set_threads(8)
+    f0 = base.reshape(h, w, 2)
+    want = O.sobel3(O.convert_to(O.bgr_to_gray(O.yuyv_to_bgr(f0)), np.float32))["mag"]
+    O.set_threads(1)
+    ok = bool((dst[0].to_numpy() == want).all())
+    R.imgproc.set_option("yuyvsobel.force_chain", 1)
+    ms_chain = timeit(lambda: R.imgproc.yuyv_to_sobel_mag_batch(src, dst))
+    R.imgproc.set_option("yuyvsobel.force_chain", 0)
+    ok_chain = bool((dst[0].to_numpy() == want).all())
+    report(f"chain YUYV->BGR->Gray->f32->Sobel magnitude 1920x1080 x{n}, fused kernel", ms, n * h * w, 6,
+           {"parity_frame0": ok, "unfused_3_kernel_chain_ms": ms_chain, "unfused_parity_frame0": ok_chain,
+            "speedup_vs_unfused": ms_chain / ms})
+    src.free(); dst.free()
+
+
+def cfg5sweep(n=8):
+    """warpAffine tile height sweep (warp.tile_rows = 32 / 48 / 64 / automatic), parity of frame 0 each time."""
+    s = 4096
+    src, dst = R.Mat.device_batch(n, s, s, 1, R.F32), R.Mat.device_batch(n, s, s, 1, R.F32)
+    base = O.fill_f32(5, s * s)
+    fill_batch(src, lambda i: (np.roll(base, i * 31) if i else base).reshape(s, s))
+    O.set_threads(len(os.sched_getaffinity(0)))
+    for ang in (15.0, 90.0, 33.0):
+        M = R.imgproc.get_rotation_matrix_2d(((s - 1) / 2, (s - 1) / 2), ang)
+        want = O.warp_affine(base.reshape(s, s), M.ravel())
+        for th in (32, 48, 64, 0):
+            R.imgproc.set_option("warp.tile_rows", th)
+            ms = timeit(lambda: R.imgproc.warp_affine_batch(src, dst, M), steps=10)
+            got = dst[0].to_numpy()
+            ok = bool((got == want).all())
+            report(f"cfg5 warpAffine {ang:g}deg 4096x4096 f32 x{n} tile_rows={th}", ms, n * s * s, 7.6, {"bit_exact_frame0": ok})
+    R.imgproc.set_option("warp.tile_rows", 0)
+    O.set_threads(1)
+    # u8 BGR 4K, 15 degrees
+    h, w = 2160, 3840
+    src8, dst8 = R.Mat.device_batch(n, h, w, 3), R.Mat.device_batch(n, h, w, 3)
+    b8 = O.fill_u8(5, h * w * 3)
+    fill_batch(src8, lambda i: np.roll(b8, i * 31).reshape(h, w, 3))
+    M = R.imgproc.get_rotation_matrix_2d(((w - 1) / 2, (h - 1) / 2), 15.0)
+    for th in (32, 48, 64, 0):
+        R.imgproc.set_option("warp.tile_rows", th)
+        ms = timeit(lambda: R.imgproc.warp_affine_batch(src8, dst8, M), steps=10)
+        report(f"warpAffine 15deg 3840x2160 BGR u8 x{n} tile_rows={th}", ms, n * h * w, 6, {})
+    R.imgproc.set_option("warp.tile_rows", 0)
+    src.free(); dst.free(); src8.free(); dst8.free()
+
+
+ALL = {"chain": chain, "cfg5sweep": cfg5sweep, "cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
        "cfg4full": lambda: cfg4(256), "cfg5full": lambda: cfg5(64)}
 for name in (sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]):
     ALL[name]()

@@ -939,3 +939,107 @@ def test_convert_to_and_gray_sobel_chain(rcv, oracle, where):
     R.imgproc.sobel_mag(gf, m)
     want = oracle.sobel3(oracle.convert_to(oracle.bgr_to_gray(bgr), np.float32, 1.0 / 255.0))["mag"]
     assert_f32(m.to_numpy(), want, f"gray->f32->sobel {where}", max_ulp=1)
+
+
+# ---- fused decode -> process chain ---------------------------------------
+def _yuyv_sobel_oracle(oracle, yuyv):
+    """The chain's stand-alone stages on the CPU: reference BT.601 -> OpenCV gray -> f32 -> Sobel magnitude."""
+    gray = oracle.bgr_to_gray(oracle.yuyv_to_bgr(yuyv))
+    return oracle.sobel3(oracle.convert_to(gray, np.float32))["mag"]
+
+
+@pytest.mark.parametrize("where", WHERE)
+@pytest.mark.parametrize("shape", [(48, 240), (270, 480), (37, 254), (64, 722), (9, 8), (5, 6), (480, 640), (21, 1218)])
+def test_yuyv_to_sobel_mag_fused(rcv, oracle, where, shape):
+    """One kernel (YuyvSobelOp on the strip pipeline) against the four-stage oracle chain: exact integer stages
+    and a correctly rounded sqrtf, so 0 ULP is demanded (the north star allows 1)."""
+    R = rcv
+    h, w = shape
+    yuyv = oracle.fill_u8(300 + h + w, h * w * 2).reshape(h, w, 2)
+    s = mats(R, yuyv, where)
+    m = out_like(R, s, where, channels=1, depth=R.F32)
+    R.imgproc.yuyv_to_sobel_mag(s, m)
+    assert_f32(m.to_numpy(), _yuyv_sobel_oracle(oracle, yuyv), f"yuyv->sobel {shape} {where}", max_ulp=0)
+
+
+def test_yuyv_to_sobel_mag_flat_and_saturated(rcv, oracle):
+    """Flat regions give gx = gy = 0 (the one input outside the fast sqrt's range); saturated chroma exercises
+    both clamp directions of the BT.601 stage."""
+    R = rcv
+    h, w = 40, 496
+    yuyv = np.zeros((h, w, 2), np.uint8)
+    yuyv[:, :, 0] = 128
+    yuyv[:, :, 1] = 128
+    yuyv[10:20, 100:300, 0] = 255
+    yuyv[10:20, 100:300, 1] = 255
+    yuyv[25:33, 8:40, :] = 0
+    yuyv[:, 480:, 0] = np.arange(16, dtype=np.uint8) * 17
+    s = R.Mat.from_numpy(yuyv).upload()
+    m = s.like(channels=1, depth=R.F32)
+    R.imgproc.yuyv_to_sobel_mag(s, m)
+    got = m.to_numpy()
+    assert_f32(got, _yuyv_sobel_oracle(oracle, yuyv), "yuyv->sobel flat", max_ulp=0)
+    assert (got[0:8, 0:90] == 0).all()
+
+
+def test_yuyv_to_sobel_mag_equals_unfused_library_chain(rcv, oracle):
+    """The fused kernel and the library's own chain of stand-alone kernels (forced) agree bit for bit; padded
+    host steps are honoured."""
+    R = rcv
+    h, w = 131, 1000
+    yuyv = oracle.fill_u8(77, h * w * 2).reshape(h, w, 2)
+    want = _yuyv_sobel_oracle(oracle, yuyv)
+    s = R.Mat.from_numpy(yuyv).upload()
+    a = s.like(channels=1, depth=R.F32)
+    R.imgproc.yuyv_to_sobel_mag(s, a)
+    n0 = R.imgproc.launch_count()
+    R.imgproc.set_option("yuyvsobel.force_chain", 1)
+    try:
+        b = s.like(channels=1, depth=R.F32)
+        R.imgproc.yuyv_to_sobel_mag(s, b)
+    finally:
+        R.imgproc.set_option("yuyvsobel.force_chain", 0)
+    assert R.imgproc.launch_count() - n0 == 3, "the forced chain is three kernels (YUYV2GRAY, convertTo, Sobel)"
+    n0 = R.imgproc.launch_count()
+    c = s.like(channels=1, depth=R.F32)
+    R.imgproc.yuyv_to_sobel_mag(s, c)
+    assert R.imgproc.launch_count() - n0 == 1, "the fused path is ONE kernel"
+    assert_f32(a.to_numpy(), want, "fused", max_ulp=0)
+    assert_f32(b.to_numpy(), want, "chain", max_ulp=0)
+    assert_f32(c.to_numpy(), want, "fused again", max_ulp=0)
+    # host Mats with padded steps on both sides
+    hs = R.Mat.from_numpy_strided(yuyv, w * 2 + 24)
+    hd = R.Mat.from_numpy_strided(np.zeros((h, w), np.float32), w * 4 + 36)
+    R.imgproc.yuyv_to_sobel_mag(hs, hd)
+    assert_f32(hd.to_numpy(), want, "host padded", max_ulp=0)
+
+
+def test_yuyv_to_sobel_mag_batch_and_errors(rcv, oracle):
+    R = rcv
+    n, h, w = 5, 72, 960
+    src = R.Mat.device_batch(n, h, w, 2)
+    dst = R.Mat.device_batch(n, h, w, 1, R.F32)
+    frames = [oracle.fill_u8(500 + j, h * w * 2).reshape(h, w, 2) for j in range(n)]
+    for j in range(n):
+        upload_into(R, frames[j], src[j])
+    n0 = R.imgproc.launch_count()
+    R.imgproc.yuyv_to_sobel_mag_batch(src, dst)
+    assert R.imgproc.launch_count() - n0 == 1
+    for j in range(n):
+        assert_f32(dst[j].to_numpy(), _yuyv_sobel_oracle(oracle, frames[j]), f"batch frame {j}", max_ulp=0)
+    src.free(); dst.free()
+    # host batch through the staging ring
+    hs = [R.Mat.from_numpy(f) for f in frames]
+    hd = [R.Mat.new(h, w, 1, R.F32) for _ in frames]
+    R.imgproc.yuyv_to_sobel_mag_batch(hs, hd)
+    for j in range(n):
+        assert_f32(hd[j].to_numpy(), _yuyv_sobel_oracle(oracle, frames[j]), f"host batch frame {j}", max_ulp=0)
+    # contract: odd widths, wrong channel counts and wrong destination geometry are errors, not silent returns
+    from rustcv_b200 import _ffi as F
+    odd = R.Mat.from_numpy(np.zeros((8, 9, 2), np.uint8))
+    for bad_src, bad_dst, code in ((odd, R.Mat.new(8, 9, 1, R.F32), F.RCV_ERR_SIZE),
+                                   (R.Mat.new(8, 8, 3), R.Mat.new(8, 8, 1, R.F32), F.RCV_ERR_DEPTH),
+                                   (R.Mat.new(8, 8, 2), R.Mat.new(8, 8, 1), F.RCV_ERR_DEPTH),
+                                   (R.Mat.new(8, 8, 2), R.Mat.new(8, 10, 1, R.F32), F.RCV_ERR_SIZE)):
+        rc = F.lib.rcv_yuyv_to_sobel_mag(C.byref(bad_src.c()), C.byref(bad_dst.c()))
+        assert rc == code, (rc, code, F.lib.rcv_last_error())
