@@ -285,7 +285,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=32, help="4K frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=16, help="host frames per GPU per e2e step")
+    ap.add_argument("--e2e-frames", type=int, default=32, help="host frames per GPU per e2e step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -121,21 +121,186 @@ int copy_out(const RcvMat *m, const Staged &st, cudaStream_t s, int written_cols
   return RCV_OK;
 }
 
+// Zero-copy: a pinned host Mat (rcv_pinned_alloc: cudaHostAlloc, one address for CPU and GPU under UVA) can be
+// read by TMA and written by the kernels' 128-bit stores directly over PCIe -- no staging copy, no HBM round
+// trip, reads and writes in flight together.  Only for 16-byte aligned Mats (the TMA / vector paths); mode is
+// the "host.zero_copy" option: 0 = never (stage through HBM), 1 = whenever both sides qualify.
+bool zero_copy_mat(const RcvMat *m) {
+  if (m->loc == RCV_DEVICE) return true;
+  return m->loc == RCV_HOST_PINNED && m->rows > 0 && m->cols > 0 && ((((uintptr_t)m->data) | m->step) & 15) == 0;
+}
+bool zero_copy_pair(const RcvMat *src, const RcvMat *dst) {
+  return opt_get("host.zero_copy", 0) != 0 && zero_copy_mat(src) && zero_copy_mat(dst);
+}
+
+// ---- the host pipeline ------------------------------------------------------------------------
+// How an op may be cut into row bands, so that the H2D copy, the kernel and the D2H copy of ONE frame overlap
+// (a single 4K BGR frame is 0.5 ms of PCIe time each way: run back to back the synchronous call costs the
+// sum, banded it costs about the larger of the two).
+struct Banding {
+  int halo = -1;         // source rows needed above / below an output band; < 0: the op cannot be banded
+  bool subview = false;  // pointwise op: a band is just a sub-image (no row-window support needed in the kernel)
+};
+constexpr Banding kNoBands = {-1, false};
+inline Banding band_window(int halo) { return Banding{halo, false}; }
+constexpr Banding kBandPointwise = {0, true};
+
+int copy_in_rows(const RcvMat *m, const Staged &st, int r0, int r1, cudaStream_t s) {
+  if (!st.staged || r1 <= r0 || m->cols == 0) return RCV_OK;
+  if (m->step == st.v.step && m->step == mat_row_bytes(m)) {  // both sides packed at one pitch: a flat copy
+    RCV_CUDA(cudaMemcpyAsync(st.v.data + (size_t)r0 * st.v.step, (const uint8_t *)m->data + (size_t)r0 * m->step,
+                             (size_t)(r1 - r0) * m->step, cudaMemcpyHostToDevice, s));
+    return RCV_OK;
+  }
+  RCV_CUDA(cudaMemcpy2DAsync(st.v.data + (size_t)r0 * st.v.step, st.v.step, (const uint8_t *)m->data + (size_t)r0 * m->step,
+                             m->step, mat_row_bytes(m), r1 - r0, cudaMemcpyHostToDevice, s));
+  return RCV_OK;
+}
+
+int copy_out_rows(const RcvMat *m, const Staged &st, int r0, int r1, cudaStream_t s, int written_cols) {
+  if (!st.staged || r1 <= r0 || m->cols == 0) return RCV_OK;
+  size_t rb = mat_row_bytes(m);
+  if (written_cols >= 0 && written_cols < m->cols) rb = (size_t)written_cols * m->channels * elem_size(m->depth);
+  if (rb == 0) return RCV_OK;
+  if (m->step == st.v.step && m->step == rb) {
+    RCV_CUDA(cudaMemcpyAsync((uint8_t *)m->data + (size_t)r0 * m->step, st.v.data + (size_t)r0 * st.v.step,
+                             (size_t)(r1 - r0) * m->step, cudaMemcpyDeviceToHost, s));
+    return RCV_OK;
+  }
+  RCV_CUDA(cudaMemcpy2DAsync((uint8_t *)m->data + (size_t)r0 * m->step, m->step, st.v.data + (size_t)r0 * st.v.step,
+                             st.v.step, rb, r1 - r0, cudaMemcpyDeviceToHost, s));
+  return RCV_OK;
+}
+
+// Rows per band for this src/dst pair, 0 = do not band.  Only pinned host memory overlaps (the driver stages
+// pageable copies itself).  Measured on a 4K BGR frame (profiles/r1_host_pipeline.txt): every band costs
+// ~20-40 us of stream hand-offs, so few large bands win -- 6 MB bands (4 per frame) 0.72-0.78 ms against
+// 0.93 ms unbanded and 0.95 ms with 1 MB bands.
+int pick_host_band_rows(const RcvMat *src, const RcvMat *dst, const Banding &bd) {
+  if (bd.halo < 0 || src->rows != dst->rows || src->rows <= 0) return 0;
+  if (!is_host(src) && !is_host(dst)) return 0;
+  if ((is_host(src) && src->loc != RCV_HOST_PINNED) || (is_host(dst) && dst->loc != RCV_HOST_PINNED)) return 0;
+  const int64_t band_bytes = opt_get("host.band_bytes", 6 << 20);
+  if (band_bytes <= 0) return 0;
+  size_t rb = mat_row_bytes(src) > mat_row_bytes(dst) ? mat_row_bytes(src) : mat_row_bytes(dst);
+  if (rb == 0) return 0;
+  int64_t br = band_bytes / (int64_t)rb;
+  if (br < 8) br = 8;
+  br = (br + 7) & ~(int64_t)7;
+  if ((int64_t)src->rows < 2 * br) return 0;
+  return (int)br;
+}
+
+// One frame through ring slot k: H2D on s_in, kernel on the library stream, D2H on s_out, chained by events.
+// band_rows > 0: the three stages run band by band (copy rows [.., r1 + halo) in, produce rows [r0, r1), copy
+// them out); 0: whole frame at once.  `in` / `out` are whole-frame views (staged scratch or the Mat itself).
+template <class F>
+int pipeline_frame(Ctx *c, const RcvMat *src, RcvMat *dst, const Staged &in, const Staged &out, int k, bool wait_slot,
+                   int band_rows, const Banding &bd, F &launch, int written_cols) {
+  const int rows = dst->rows;
+  const int br = band_rows > 0 ? band_rows : (rows > 0 ? rows : 1);
+  int uploaded = 0;
+  for (int r0 = 0; r0 == 0 || r0 < rows; r0 += br) {
+    const int r1 = r0 + br < rows ? r0 + br : rows;
+    if (r0 == 0 && wait_slot) RCV_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_out[k], 0));  // slot k fully drained
+    int need = band_rows > 0 ? r1 + bd.halo : src->rows;
+    if (need > src->rows) need = src->rows;
+    if (need > uploaded) {
+      RCV_TRY(copy_in_rows(src, in, uploaded, need, c->s_in));
+      uploaded = need;
+    }
+    RCV_CUDA(cudaEventRecord(c->ev_in[k], c->s_in));
+    RCV_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+    DBatch sb = single(in.v), db = single(out.v);
+    if (band_rows > 0) {
+      if (bd.subview) {
+        sb.v.data += (size_t)r0 * sb.v.step;
+        db.v.data += (size_t)r0 * db.v.step;
+        sb.v.rows = db.v.rows = r1 - r0;
+      } else {
+        db.y0 = r0;
+        db.y1 = r1;
+      }
+    }
+    RCV_TRY(launch(c, sb, db, c->stream));
+    RCV_CUDA(cudaEventRecord(c->ev_k[k], c->stream));
+    RCV_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+    RCV_TRY(copy_out_rows(dst, out, r0, r1, c->s_out, written_cols));
+  }
+  RCV_CUDA(cudaEventRecord(c->ev_out[k], c->s_out));
+  return RCV_OK;
+}
+
+int sync_pipeline(Ctx *c) {
+  RCV_CUDA(cudaStreamSynchronize(c->s_out));
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  RCV_CUDA(cudaStreamSynchronize(c->s_in));
+  return RCV_OK;
+}
+
+// srcs[i] -> dsts[i] with at least one side in host memory: software pipeline over the staging ring.
+template <class F>
+int run_host_pipeline(Ctx *c, const RcvMat *srcs, RcvMat *dsts, int n, F &launch, int written_cols, const Banding &bd) {
+  Staged si[kRing], so[kRing];
+  const int depth = n < kRing ? n : kRing;
+  // Direct write (option "host.direct_write", OFF by default): a pinned, 16-byte aligned destination written by
+  // the kernel itself over PCIe.  Measured (profiles/r1_host_pipeline.txt): the Gaussian strip kernel alone
+  // stores to host memory at 49 GB/s (whole 480-byte row segments), the rate of the D2H copy it would replace,
+  // but next to a concurrent H2D copy the pair reaches only 41 GB/s each way against 44-45 GB/s for two copy
+  // engines, and kernels with narrower stores (YUYV->BGR: 48 B per thread) drop to a third.  TMA reads straight
+  // from host memory ("host.zero_copy") reach 34-38 GB/s.  The copy engines stay the default on both sides.
+  bool direct = opt_get("host.direct_write", 0) != 0 && is_host(&dsts[0]);
+  for (int i = 0; i < n && direct; ++i) direct = zero_copy_mat(&dsts[i]);
+  for (int k = 0; k < depth; ++k) {
+    RCV_TRY(stage_alloc(c, &srcs[k], SCR_STAGE_IN0 + k, &si[k]));
+    if (direct)
+      so[k].staged = false;
+    else
+      RCV_TRY(stage_alloc(c, &dsts[k], SCR_STAGE_OUT0 + 3 * k, &so[k]));
+  }
+  RCV_CUDA(cudaStreamSynchronize(c->stream));
+  int band_rows = pick_host_band_rows(&srcs[0], &dsts[0], bd);
+  for (int i = 0; i < n; ++i) {
+    const int k = i % kRing;
+    Staged in = si[k], out = so[k];
+    if (!in.staged) in.v = view_of(&srcs[i], srcs[i].data, srcs[i].step);
+    if (!out.staged) out.v = view_of(&dsts[i], dsts[i].data, dsts[i].step);
+    // inside a batch the frames themselves overlap; only the pipeline's fill (first frame) and drain (last
+    // frame) gain from bands, and the interior frames are spared the per-band hand-offs
+    const int br = (i == 0 || i == n - 1) ? band_rows : 0;
+    int rc = pipeline_frame(c, &srcs[i], &dsts[i], in, out, k, i >= kRing, br, bd, launch, written_cols);
+    if (rc == RCV_ERR_UNSUPPORTED && br > 0) {
+      // the op fell off its row-window capable kernel for this geometry: redo the frame unbanded
+      RCV_TRY(sync_pipeline(c));
+      band_rows = 0;
+      rc = pipeline_frame(c, &srcs[i], &dsts[i], in, out, k, false, 0, bd, launch, written_cols);
+    }
+    if (rc != RCV_OK) {
+      sync_pipeline(c);
+      return rc;
+    }
+  }
+  return sync_pipeline(c);
+}
+
 // Runs `launch(ctx, src_batch, dst_batch, stream)` for one src -> one dst.
 template <class F>
-int run_unary(const RcvMat *src, RcvMat *dst, F launch, int written_cols = -1) {
+int run_unary(const RcvMat *src, RcvMat *dst, F launch, int written_cols = -1, Banding bd = kNoBands) {
   const RcvMat *mats[2] = {src, dst};
   Ctx *c = pick_ctx(mats, 2);
   if (!c) return RCV_ERR_NOT_INIT;
   std::lock_guard<std::mutex> lk(c->mu);
-  Staged si, so;
-  RCV_TRY(stage_alloc(c, src, SCR_STAGE_IN0, &si));
-  RCV_TRY(stage_alloc(c, dst, SCR_STAGE_OUT0, &so));
-  RCV_TRY(copy_in(src, si, c->stream));
-  RCV_TRY(launch(c, single(si.v), single(so.v), c->stream));
-  RCV_TRY(copy_out(dst, so, c->stream, written_cols));
-  if (ctx_blocking() || si.staged || so.staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
-  return RCV_OK;
+  if (!is_host(src) && !is_host(dst)) {
+    RCV_TRY(launch(c, single(view_of(src, src->data, src->step)), single(view_of(dst, dst->data, dst->step)), c->stream));
+    if (ctx_blocking()) RCV_CUDA(cudaStreamSynchronize(c->stream));
+    return RCV_OK;
+  }
+  if (zero_copy_pair(src, dst)) {
+    RCV_TRY(launch(c, single(view_of(src, src->data, src->step)), single(view_of(dst, dst->data, dst->step)), c->stream));
+    RCV_CUDA(cudaStreamSynchronize(c->stream));  // host-visible results: always synchronous
+    return RCV_OK;
+  }
+  return run_host_pipeline(c, src, dst, 1, launch, written_cols, bd);
 }
 
 // Batches.  Device Mats with a uniform frame stride: one launch.  Device Mats otherwise:
@@ -164,7 +329,7 @@ int check_batch_geometry(const RcvMat *m, int n, const char *name) {
 }
 
 template <class F>
-int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch, int written_cols = -1) {
+int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch, int written_cols = -1, Banding bd = kNoBands) {
   if (n == 0) return RCV_OK;
   std::vector<const RcvMat *> mats;
   for (int i = 0; i < n; ++i) {
@@ -187,33 +352,18 @@ int run_batch(const RcvMat *srcs, RcvMat *dsts, int n, F launch, int written_col
     if (ctx_blocking()) RCV_CUDA(cudaStreamSynchronize(c->stream));
     return RCV_OK;
   }
-  // host-resident (either side): software pipeline over the staging ring
-  Staged si[kRing], so[kRing];
-  const int depth = n < kRing ? n : kRing;
-  for (int k = 0; k < depth; ++k) {
-    RCV_TRY(stage_alloc(c, &srcs[k], SCR_STAGE_IN0 + k, &si[k]));
-    RCV_TRY(stage_alloc(c, &dsts[k], SCR_STAGE_OUT0 + 3 * k, &so[k]));
+  if (zero_copy_pair(&srcs[0], &dsts[0])) {  // geometry and location are uniform over the batch (checked)
+    bool all = true;
+    for (int i = 0; i < n; ++i) all = all && zero_copy_mat(&srcs[i]) && zero_copy_mat(&dsts[i]);
+    if (all) {
+      for (int i = 0; i < n; ++i)
+        RCV_TRY(launch(c, single(view_of(&srcs[i], srcs[i].data, srcs[i].step)),
+                       single(view_of(&dsts[i], dsts[i].data, dsts[i].step)), c->stream));
+      RCV_CUDA(cudaStreamSynchronize(c->stream));
+      return RCV_OK;
+    }
   }
-  RCV_CUDA(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < n; ++i) {
-    const int k = i % kRing;
-    Staged in = si[k], out = so[k];
-    if (!in.staged) in.v = view_of(&srcs[i], srcs[i].data, srcs[i].step);
-    if (!out.staged) out.v = view_of(&dsts[i], dsts[i].data, dsts[i].step);
-    if (i >= kRing) RCV_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_out[k], 0));  // slot k fully drained
-    RCV_TRY(copy_in(&srcs[i], in, c->s_in));
-    RCV_CUDA(cudaEventRecord(c->ev_in[k], c->s_in));
-    RCV_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
-    RCV_TRY(launch(c, single(in.v), single(out.v), c->stream));
-    RCV_CUDA(cudaEventRecord(c->ev_k[k], c->stream));
-    RCV_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
-    RCV_TRY(copy_out(&dsts[i], out, c->s_out, written_cols));
-    RCV_CUDA(cudaEventRecord(c->ev_out[k], c->s_out));
-  }
-  RCV_CUDA(cudaStreamSynchronize(c->s_out));
-  RCV_CUDA(cudaStreamSynchronize(c->stream));
-  RCV_CUDA(cudaStreamSynchronize(c->s_in));
-  return RCV_OK;
+  return run_host_pipeline(c, srcs, dsts, n, launch, written_cols, bd);
 }
 
 int check_cvt(const RcvMat *src, const RcvMat *dst, int code) {
@@ -333,7 +483,7 @@ int rcv_cvt_color(const RcvMat *src, RcvMat *dst, int32_t code) {
   RCV_TRY(check_cvt(src, dst, code));
   return run_unary(src, dst, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_cvt(c, s, d, code, st);
-  }, cvt_written_cols(src, code));
+  }, cvt_written_cols(src, code), kBandPointwise);
 }
 
 int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code) {
@@ -344,7 +494,7 @@ int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t cod
   RCV_TRY(check_cvt(&srcs[0], &dsts[0], code));
   return run_batch(srcs, dsts, n, [code](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_cvt(c, s, d, code, st);
-  }, cvt_written_cols(&srcs[0], code));
+  }, cvt_written_cols(&srcs[0], code), kBandPointwise);
 }
 
 int rcv_yuyv_to_bgr(const RcvMat *src, RcvMat *dst) { return rcv_cvt_color(src, dst, RCV_COLOR_YUYV2BGR); }
@@ -431,7 +581,7 @@ int rcv_convert_to(const RcvMat *src, RcvMat *dst, double alpha, double beta) {
   RCV_TRY(check_same_size(src, dst, "convertTo"));
   return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_convert(c, s, d, alpha, beta, st);
-  });
+  }, -1, kBandPointwise);
 }
 
 // ---- filters -------------------------------------------------------------------------------
@@ -439,7 +589,7 @@ int rcv_gaussian_blur(const RcvMat *src, RcvMat *dst, int32_t kw, int32_t kh, do
   RCV_TRY(check_filter_pair(src, dst, "GaussianBlur"));
   return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
-  });
+  }, -1, band_window(3));
 }
 
 int rcv_gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t kw, int32_t kh, double sigma_x,
@@ -451,7 +601,7 @@ int rcv_gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t
   RCV_TRY(check_filter_pair(&srcs[0], &dsts[0], "GaussianBlur"));
   return run_batch(srcs, dsts, n, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
-  });
+  }, -1, band_window(3));
 }
 
 int rcv_sep_filter2d(const RcvMat *src, RcvMat *dst, const float *kx, int32_t kw, const float *ky, int32_t kh) {
@@ -460,7 +610,7 @@ int rcv_sep_filter2d(const RcvMat *src, RcvMat *dst, const float *kx, int32_t kw
   if (src->depth != RCV_F32) return fail(RCV_ERR_DEPTH, "rcv_sep_filter2d is f32; use rcv_sep_filter2d_q8 for u8");
   return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_sepfilter_f32(c, s, d, kx, kw, ky, kh, st);
-  });
+  }, -1, band_window(kh / 2));
 }
 
 int rcv_sep_filter2d_q8(const RcvMat *src, RcvMat *dst, const int32_t *kx, int32_t kw, const int32_t *ky, int32_t kh) {
@@ -477,7 +627,7 @@ int rcv_filter2d(const RcvMat *src, RcvMat *dst, const float *kernel, int32_t kw
   if (!kernel) return fail(RCV_ERR_ARG, "NULL kernel");
   return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_filter2d(c, s, d, kernel, kw, kh, delta, st);
-  });
+  }, -1, band_window(kh / 2));
 }
 
 static int check_sobel(const RcvMat *src, const RcvMat *mag, const RcvMat *gx, const RcvMat *gy) {
@@ -497,6 +647,10 @@ static int check_sobel(const RcvMat *src, const RcvMat *mag, const RcvMat *gx, c
 
 int rcv_sobel_mag(const RcvMat *src, RcvMat *mag, RcvMat *gx, RcvMat *gy) {
   RCV_TRY(check_sobel(src, mag, gx, gy));
+  if (mag && !gx && !gy)  // the common case: one output, banded host pipeline
+    return run_unary(src, mag, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+      return launch_sobel(c, s, d, none_batch(), none_batch(), st);
+    }, -1, band_window(1));
   const RcvMat *mats[4] = {src, mag, gx, gy};
   Ctx *c = pick_ctx(mats, 4);
   if (!c) return RCV_ERR_NOT_INIT;
@@ -529,7 +683,7 @@ int rcv_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
   RCV_TRY(check_sobel(&srcs[0], &mags[0], nullptr, nullptr));
   return run_batch(srcs, mags, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_sobel(c, s, d, none_batch(), none_batch(), st);
-  });
+  }, -1, band_window(1));
 }
 
 // ---- geometry --------------------------------------------------------------------------------
@@ -632,7 +786,7 @@ int rcv_yuyv_to_sobel_mag(const RcvMat *src, RcvMat *mag) {
   RCV_TRY(check_yuyv_sobel(src, mag));
   return run_unary(src, mag, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_yuyv_sobel(c, s, d, st);
-  });
+  }, -1, band_window(1));
 }
 
 int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
@@ -643,7 +797,7 @@ int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
   RCV_TRY(check_yuyv_sobel(&srcs[0], &mags[0]));
   return run_batch(srcs, mags, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_yuyv_sobel(c, s, d, st);
-  });
+  }, -1, band_window(1));
 }
 
 }  // extern "C"

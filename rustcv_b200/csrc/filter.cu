@@ -185,6 +185,7 @@ int launch_sepfilter_f32(Ctx *c, const DBatch &src, const DBatch &dst, const flo
     int rc = launch_sepf32_strip(c, src, dst, kx, kw, ky, kh, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
+  if (dst.windowed()) return RCV_ERR_UNSUPPORTED;  // whole-image kernel: the caller retries without a row window
   return launch_sep<float>(src, dst, kx, kw, ky, kh, s);
 }
 
@@ -260,6 +261,7 @@ int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh
       int rc = launch_gaussq8_strip(c, src, dst, kx, ky, kw, s);
       if (rc != RCV_ERR_UNSUPPORTED) return rc;
     }
+    if (dst.windowed()) return RCV_ERR_UNSUPPORTED;
     return launch_sepfilter_q8(c, src, dst, kx, kw, ky, kh, s);
   }
   double kd[kMaxTaps + 1];
@@ -298,6 +300,7 @@ int launch_yuyv_sobel(Ctx *c, const DBatch &src, const DBatch &mag, cudaStream_t
     int rc = launch_yuyv_sobel_strip(c, src, mag, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
+  if (mag.windowed()) return RCV_ERR_UNSUPPORTED;
   DBatch g8 = mag, g32 = mag;
   const size_t p8 = ((size_t)src.v.cols + 255) / 256 * 256, p32 = ((size_t)src.v.cols * 4 + 255) / 256 * 256;
   void *a = nullptr, *b = nullptr;
@@ -405,6 +408,7 @@ int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k
                                     : launch_filter2d_u8_strip(c, src, dst, k, kw, kh, delta, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
+  if (dst.windowed()) return RCV_ERR_UNSUPPORTED;
   void *dtaps = nullptr;
   RCV_TRY(ctx_scratch(c, SCR_TAPS, (size_t)kw * kh * sizeof(float), &dtaps));
   RCV_CUDA(cudaMemcpyAsync(dtaps, k, (size_t)kw * kh * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -475,6 +479,7 @@ int launch_sobel(Ctx *c, const DBatch &src, const DBatch &mag, const DBatch &gx,
     int rc = launch_sobel_strip(c, src, mag, gx, gy, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;
   }
+  if (mag.windowed()) return RCV_ERR_UNSUPPORTED;
   if (src.v.rows > 65535 || src.n > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
   SobelArgs a;
   a.src = src.v.data;

@@ -55,6 +55,12 @@ struct DBatch {
   DView v;              // geometry + frame 0
   size_t frame_stride;  // bytes between frames (0 when n == 1)
   int n;
+  // Row window (on the DESTINATION batch of a launch): produce only output rows [y0, y1) of the image; source
+  // rows outside the window's halo need not be resident yet.  y1 == 0 means all rows.  Used by the host
+  // pipeline (abi.cu) to overlap H2D / kernel / D2H band by band inside ONE frame.  The strip launchers honour
+  // it; a dispatcher that would have to fall back to a whole-image kernel returns RCV_ERR_UNSUPPORTED instead.
+  int y0 = 0, y1 = 0;
+  bool windowed() const { return y1 > 0; }
 };
 
 // ---- context ----------------------------------------------------------------

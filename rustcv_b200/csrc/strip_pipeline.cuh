@@ -47,6 +47,7 @@ struct StripOut {
 struct StripParams {
   StripOut out[3];
   int rows;
+  int row_begin, row_end;  // output rows produced by this launch (the whole image unless the batch is windowed)
   int row_bytes;  // cols * cn * elemsize
   int strips, bands, band_rows;
   int n_frames;
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     const int band = (int)(t % p.bands);
     const int frame = (int)(t / p.bands);
     const int x0 = strip * kOutBytes;
-    const int y0 = band * p.band_rows;
-    const int y1 = min(y0 + p.band_rows, p.rows);
+    const int y0 = p.row_begin + band * p.band_rows;
+    const int y1 = min(y0 + p.band_rows, p.row_end);
     const int ys = y0 - HV;                // first row fed
     const int n_feed = (y1 - y0) + 2 * HV;  // rows fed: ys .. y1+HV-1
     const int n_chunks = (n_feed + R - 1) / R;
@@ -325,10 +326,17 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     }
   }
   p.rows = src.v.rows;
+  p.row_begin = 0;
+  p.row_end = p.rows;
+  if (outs[0].windowed()) {
+    p.row_begin = outs[0].y0 < 0 ? 0 : outs[0].y0;
+    p.row_end = outs[0].y1 > p.rows ? p.rows : outs[0].y1;
+    if (p.row_end <= p.row_begin) return RCV_OK;
+  }
   p.row_bytes = (int)src.v.row_bytes();
   p.strips = ceil_div(p.row_bytes, kOutBytes);
-  p.band_rows = pick_band_rows(c, band_opt, p.rows, p.strips, src.n, Op::HV, NW);
-  p.bands = ceil_div(p.rows, p.band_rows);
+  p.band_rows = pick_band_rows(c, band_opt, p.row_end - p.row_begin, p.strips, src.n, Op::HV, NW);
+  p.bands = ceil_div(p.row_end - p.row_begin, p.band_rows);
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
   p.next_item = nullptr;

@@ -1043,3 +1043,112 @@ def test_yuyv_to_sobel_mag_batch_and_errors(rcv, oracle):
                                    (R.Mat.new(8, 8, 2), R.Mat.new(8, 10, 1, R.F32), F.RCV_ERR_SIZE)):
         rc = F.lib.rcv_yuyv_to_sobel_mag(C.byref(bad_src.c()), C.byref(bad_dst.c()))
         assert rc == code, (rc, code, F.lib.rcv_last_error())
+
+
+# ---- banded host pipeline: H2D / kernel / D2H of ONE frame overlap band by band ----------------------
+@pytest.fixture
+def small_bands(rcv):
+    """Bands of 24 KB so that test-sized images are cut into many bands (default: 6 MB)."""
+    rcv.imgproc.set_option("host.band_bytes", 24 << 10)
+    yield rcv
+    rcv.imgproc.set_option("host.band_bytes", 6 << 20)
+
+
+def _pinned_pair(R, a, channels=None, depth=None):
+    s = mats(R, a, "pinned")
+    d = s.like(channels=channels, depth=depth)
+    d.data[:] = 0x5A
+    return s, d
+
+
+def test_banded_pipeline_matches_oracle(small_bands, oracle):
+    """Every op that declares a row window (strip kernels) or is pointwise, on pinned host Mats cut into
+    8..40-row bands: identical to the oracle, band seams included."""
+    R = small_bands
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, size=(333, 500, 3), dtype=np.uint8)
+    for ks, sg in (((5, 5), 0.0), ((3, 3), 0.0), ((7, 7), 1.5), ((5, 5), 1.1)):
+        s, d = _pinned_pair(R, bgr)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.gaussian_blur(s, d, ks, sg)
+        assert R.imgproc.launch_count() - n0 > 4, "expected one launch per band"
+        assert_same(d.to_numpy(), oracle.gaussian_blur(bgr, ks, sg), f"banded gaussian {ks} {sg}")
+    gray = rng.integers(0, 256, size=(301, 777), dtype=np.uint8)
+    s, d = _pinned_pair(R, gray)
+    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(gray, (5, 5), 0.0), "banded gaussian gray")
+    f = rng.random(size=(257, 640), dtype=np.float32)
+    s, d = _pinned_pair(R, f)
+    R.imgproc.sobel_mag(s, d)
+    assert_f32(d.to_numpy(), oracle.sobel3(f)["mag"], "banded sobel", max_ulp=1)
+    kx = np.array([0.25, 0.5, 0.25], np.float32)
+    ky = np.array([0.1, 0.2, 0.4, 0.2, 0.1], np.float32)
+    for k1, k2 in ((kx, kx), (ky, ky)):
+        s, d = _pinned_pair(R, f)
+        R.imgproc.sep_filter2d(s, d, k1, k2)
+        assert_f32(d.to_numpy(), oracle.sepfilter_f32(f, k1, k2), "banded sepfilter f32", max_ulp=0)
+    k33 = rng.random(size=(3, 3), dtype=np.float32) - 0.4
+    s, d = _pinned_pair(R, f)
+    R.imgproc.filter2d(s, d, k33, 0.25)
+    assert_f32(d.to_numpy(), oracle.filter2d(f, k33, 0.25), "banded filter2d f32", max_ulp=0)
+    s, d = _pinned_pair(R, bgr)
+    R.imgproc.filter2d(s, d, k33, 1.0)
+    assert_same(d.to_numpy(), oracle.filter2d(bgr, k33, 1.0), "banded filter2d u8")
+    # pointwise ops: bands are sub-images
+    yuyv = rng.integers(0, 256, size=(240, 322, 2), dtype=np.uint8)
+    s, d = _pinned_pair(R, yuyv, channels=3)
+    R.imgproc.cvt_color(s, d, R.imgproc.COLOR_YUYV2BGR)
+    assert_same(d.to_numpy(), oracle.yuyv_to_bgr(yuyv), "banded yuyv->bgr")
+    s, d = _pinned_pair(R, bgr, channels=1)
+    R.imgproc.cvt_color(s, d, R.imgproc.COLOR_BGR2GRAY)
+    assert_same(d.to_numpy(), oracle.bgr_to_gray(bgr), "banded bgr->gray")
+    s, d = _pinned_pair(R, bgr, depth=R.F32)
+    R.imgproc.convert_to(s, d, R.F32, 0.5, 1.0)
+    assert_f32(d.to_numpy().reshape(333, -1), oracle.convert_to(bgr, np.float32, 0.5, 1.0).reshape(333, -1), "banded convertTo", max_ulp=0)
+    s, d = _pinned_pair(R, yuyv, channels=1, depth=R.F32)
+    R.imgproc.yuyv_to_sobel_mag(s, d)
+    assert_f32(d.to_numpy(), _yuyv_sobel_oracle(oracle, yuyv), "banded yuyv->sobel", max_ulp=0)
+
+
+def test_banded_pipeline_fallback_and_mixed_locations(small_bands, oracle):
+    """A kernel size only the whole-image kernels cover (9x9) silently takes the unbanded path; pinned -> device
+    and device -> pinned pairs band one side only; batches of pinned frames band inside every frame."""
+    R = small_bands
+    rng = np.random.default_rng(6)
+    bgr = rng.integers(0, 256, size=(200, 400, 3), dtype=np.uint8)
+    s, d = _pinned_pair(R, bgr)
+    R.imgproc.gaussian_blur(s, d, (9, 9), 2.0)
+    assert_same(d.to_numpy(), oracle.gaussian_blur(bgr, (9, 9), 2.0), "9x9 falls back to the unbanded path")
+    want = oracle.gaussian_blur(bgr, (5, 5), 0.0)
+    dev_dst = R.Mat.from_numpy(np.zeros_like(bgr)).upload()
+    R.imgproc.gaussian_blur(s, dev_dst, (5, 5), 0.0)
+    assert_same(dev_dst.to_numpy(), want, "pinned -> device")
+    dev_src = R.Mat.from_numpy(bgr).upload()
+    _, d2 = _pinned_pair(R, bgr)
+    R.imgproc.gaussian_blur(dev_src, d2, (5, 5), 0.0)
+    assert_same(d2.to_numpy(), want, "device -> pinned")
+    frames = [rng.integers(0, 256, size=(150, 320, 3), dtype=np.uint8) for _ in range(7)]
+    hs = [mats(R, f, "pinned") for f in frames]
+    hd = [m.like() for m in hs]
+    R.imgproc.gaussian_blur_batch(hs, hd, (5, 5), 0.0)
+    for j, f in enumerate(frames):
+        assert_same(hd[j].to_numpy(), oracle.gaussian_blur(f, (5, 5), 0.0), f"banded batch frame {j}")
+    # direct write: the kernel stores straight into the pinned destination (optional path, off by default)
+    R.imgproc.set_option("host.direct_write", 1)
+    try:
+        _, d3 = _pinned_pair(R, bgr)
+        R.imgproc.gaussian_blur(s, d3, (5, 5), 0.0)
+        assert_same(d3.to_numpy(), want, "pinned, direct write")
+        R.imgproc.set_option("host.zero_copy", 1)
+        _, d4 = _pinned_pair(R, bgr)
+        R.imgproc.gaussian_blur(s, d4, (5, 5), 0.0)
+        assert_same(d4.to_numpy(), want, "pinned, zero copy both ways")
+    finally:
+        R.imgproc.set_option("host.direct_write", 0)
+        R.imgproc.set_option("host.zero_copy", 0)
+    # pageable Mats never band (the driver stages those copies itself)
+    n0 = R.imgproc.launch_count()
+    hp = R.Mat.empty()
+    R.imgproc.gaussian_blur(R.Mat.from_numpy(bgr), hp, (5, 5), 0.0)
+    assert R.imgproc.launch_count() - n0 == 1
+    assert_same(hp.to_numpy(), want, "pageable")
