@@ -172,7 +172,8 @@ RCV_API int rcv_get_rotation_matrix_2d(double cx, double cy, double angle_deg, d
 RCV_API int rcv_invert_affine(const double M[6], double iM[6]);
 
 /* ---- fused chains (the step upstream of every imgproc call) ------------- */
-/* GaussianBlur5x5(YUYV2BGR(src)) without the intermediate BGR round trip. */
+/* GaussianBlur5x5(YUYV2BGR(src)) in ONE kernel (2 B/px in, 3 B/px out instead of
+ * the two kernels' 11 B/px); bit-identical to rcv_yuyv_to_bgr + rcv_gaussian_blur. */
 RCV_API int rcv_yuyv_to_bgr_gaussian5(const RcvMat *src_yuyv, RcvMat *dst_bgr);
 /* SobelMagnitude(convertTo_f32(BGR2GRAY(YUYV2BGR(src)))) in ONE kernel: the raw
  * camera frame (rustcv/src/videoio/mod.rs:201-205, channels=2, even cols) in,
@@ -192,6 +193,7 @@ RCV_API int rcv_warp_affine_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, c
                           int32_t inverse_map, double border_value);
 RCV_API int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code);
 RCV_API int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs_yuyv, RcvMat *mags_f32, int32_t n);
+RCV_API int rcv_yuyv_to_bgr_gaussian5_batch(const RcvMat *srcs_yuyv, RcvMat *dsts_bgr, int32_t n);
 
 /* ---- tuning knobs (benchmark/diagnostic use) ----------------------------- */
 /* name/value integer options, e.g. "gauss.band_rows", "gauss.variant". */

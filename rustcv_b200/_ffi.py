@@ -84,6 +84,7 @@ SIGNATURES = {
     "rcv_yuyv_to_bgr_gaussian5": [_MatP, _MatP],
     "rcv_yuyv_to_sobel_mag": [_MatP, _MatP],
     "rcv_yuyv_to_sobel_mag_batch": [_MatP, _MatP, C.c_int32],
+    "rcv_yuyv_to_bgr_gaussian5_batch": [_MatP, _MatP, C.c_int32],
     "rcv_gaussian_blur_batch": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double],
     "rcv_sobel_mag_batch": [_MatP, _MatP, C.c_int32],
     "rcv_resize_bilinear_batch": [_MatP, _MatP, C.c_int32],

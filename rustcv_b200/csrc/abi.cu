@@ -770,7 +770,18 @@ int rcv_yuyv_to_bgr_gaussian5(const RcvMat *src, RcvMat *dst) {
   RCV_TRY(check_cvt(src, dst, RCV_COLOR_YUYV2BGR));
   return run_unary(src, dst, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_yuyv_gauss5(c, s, d, st);
-  });
+  }, -1, band_window(2));
+}
+
+int rcv_yuyv_to_bgr_gaussian5_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n) {
+  if (n < 0 || (n > 0 && (!srcs || !dsts))) return fail(RCV_ERR_ARG, "bad batch arguments");
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_batch_geometry(srcs, n, "srcs"));
+  RCV_TRY(check_batch_geometry(dsts, n, "dsts"));
+  RCV_TRY(check_cvt(&srcs[0], &dsts[0], RCV_COLOR_YUYV2BGR));
+  return run_batch(srcs, dsts, n, [](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_yuyv_gauss5(c, s, d, st);
+  }, -1, band_window(2));
 }
 
 static int check_yuyv_sobel(const RcvMat *src, const RcvMat *mag) {

@@ -273,10 +273,18 @@ int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh
   return launch_sepfilter_f32(c, src, dst, kx, kw, ky, kh, s);
 }
 
-// YUYV -> BGR -> GaussianBlur 5x5.  Two kernels over a device-resident intermediate (no
-// host round trip); the single-kernel fusion is SURVEY.md section 8f rank 1.
+// YUYV -> BGR -> GaussianBlur 5x5.  One fused strip kernel
+// (strip_yuyv_gauss5.cu) whenever the strip path applies; otherwise (tiny, odd-width or unaligned images) the
+// two stand-alone kernels over a device-resident intermediate.
+int launch_yuyv_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+
 int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
   if (src.v.rows == 0 || src.v.cols == 0 || src.n == 0) return RCV_OK;
+  if (opt_get("yuyvgauss.force_chain", 0) == 0) {
+    int rc = launch_yuyv_gauss5_strip(c, src, dst, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
+  if (dst.windowed()) return RCV_ERR_UNSUPPORTED;
   DBatch tmp = dst;
   size_t pitch = (dst.v.row_bytes() + 255) / 256 * 256;
   size_t frame = pitch * (size_t)dst.v.rows;

@@ -8,25 +8,6 @@ namespace rcv {
 //   out = (sum_ij k_i k_j p + 128) >> 8, k = {1,4,6,4,1}   (oracle: orc_sepfilter_u8_q8
 //   with Q8 taps {16,64,96,64,16}: (sum ky kx p + 32768) >> 16 is the same number)
 // ---------------------------------------------------------------------------------------
-// Integer ops pinned with inline PTX so that NVVM cannot re-associate the sums (it turns
-// the 4-op forms below into 5): ptxas still picks the pipe (IADD3 / IMAD.IADD / LEA).
-__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-template <int M>
-__device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
-  uint32_t d;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(M), "r"(c));
-  return d;
-}
-
 template <int CN>
 struct Gauss5Op {
   static constexpr int HV = 2;   // rows of vertical halo

@@ -59,15 +59,58 @@ struct StripParams {
   float ftaps[52];                // SepF32Op: kx[0..KS) then ky[0..KS); Filter2dOp: KS*KS taps row-major, then delta
 };
 
+// ---------------------------------------------------------------------------------------
+// packed 16-bit lane arithmetic shared by the u8 ops
+// ---------------------------------------------------------------------------------------
+// Integer ops pinned with inline PTX so that NVVM cannot re-associate the sums (it turns
+// the 4-op forms below into 5): ptxas still picks the pipe (IADD3 / IMAD.IADD / LEA).
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <int M>
+__device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(M), "r"(c));
+  return d;
+}
+
 // Optional op traits (absent = 1 / 0):
-//   Op::OMUL  output bytes per input byte: a lane that owns 16 input bytes writes 16*OMUL output bytes
-//             (the fused YUYV -> Sobel op turns 8 pixels of 2 bytes into 8 floats);
+//   Op::OMUL, Op::ODIV  output bytes per input byte = OMUL / ODIV: a lane that owns 16 input bytes writes
+//             16*OMUL/ODIV output bytes (the fused YUYV ops turn 8 pixels of 2 bytes into 8 floats or 8 BGR pixels);
+//   Op::SINGLE_PATH  only the per-row-tested loop is compiled (ops whose row body is so long that a second,
+//             unpredicated copy of it would push the kernel out of the 32 KB instruction cache);
+//   Op::BAND_ROWS  output rows per work item when the job is large (default 40 - 2*HV);
+//   Op::EDGES the op applies the horizontal border itself (on its vertical sums, in registers) and is told
+//             per item where the row's edges are: op.edges(left_edge, right_edge, xr, lane);
 //   Op::MACRO horizontal border elements are macro-pixels reflected INCLUDING the edge element
 //             (element -1 <- element 0, element n <- element n-1) instead of REFLECT_101.
 template <class Op, class = void>
 struct OpOmul { static constexpr int value = 1; };
 template <class Op>
 struct OpOmul<Op, std::void_t<decltype(Op::OMUL)>> { static constexpr int value = Op::OMUL; };
+template <class Op, class = void>
+struct OpOdiv { static constexpr int value = 1; };
+template <class Op>
+struct OpOdiv<Op, std::void_t<decltype(Op::ODIV)>> { static constexpr int value = Op::ODIV; };
+template <class Op, class = void>
+struct OpEdges { static constexpr bool value = false; };
+template <class Op>
+struct OpEdges<Op, std::void_t<decltype(Op::EDGES)>> { static constexpr bool value = Op::EDGES; };
+template <class Op, class = void>
+struct OpSinglePath { static constexpr bool value = false; };
+template <class Op>
+struct OpSinglePath<Op, std::void_t<decltype(Op::SINGLE_PATH)>> { static constexpr bool value = Op::SINGLE_PATH; };
+template <class Op, class = void>
+struct OpBandRows { static constexpr int value = 5 * 8 - 2 * Op::HV; };  // 40 fed rows = 5 chunks
+template <class Op>
+struct OpBandRows<Op, std::void_t<decltype(Op::BAND_ROWS)>> { static constexpr int value = Op::BAND_ROWS; };
 template <class Op, class = void>
 struct OpMacro { static constexpr int value = 0; };
 template <class Op>
@@ -81,7 +124,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   static_assert(R == 8 && R >= 2 * Op::HV + 1, "chunk rows (the ops' window rotation assumes 8-row chunks)");
   static_assert(Op::E * (Op::P + 1) <= 16, "horizontal halo must fit the 16-byte halo lanes");
   constexpr int HV = Op::HV, P = Op::P, E = Op::E;
-  constexpr int OM = OpOmul<Op>::value, RO = OpMacro<Op>::value;
+  constexpr int OM = OpOmul<Op>::value, OD = OpOdiv<Op>::value, RO = OpMacro<Op>::value;
   constexpr uint32_t kStageBytes = R * kTileBytes;
   extern __shared__ __align__(128) uint8_t smem_raw[];
 
@@ -131,13 +174,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     // this lane's slice of the outputs
     const int xl = x0 + (lane - 1) * kLaneBytes;
     int nvalid = 0;
-    if (lane >= 1 && lane <= 30) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes) * OM;  // in OUTPUT bytes
+    if (lane >= 1 && lane <= 30) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes) * OM / OD;  // in OUTPUT bytes
     // output pointers of the next row to emit (row y0), advanced by one step per emitted row
     uint8_t *optr[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       optr[k] = (k < Op::NOUT && p.out[k].data)
-                    ? p.out[k].data + (size_t)frame * p.out[k].fs + (size_t)y0 * p.out[k].step + (long long)xl * OM
+                    ? p.out[k].data + (size_t)frame * p.out[k].fs + (size_t)y0 * p.out[k].step + (long long)xl * OM / OD
                     : nullptr;
 
     auto issue = [&](int c) {
@@ -151,6 +194,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       for (int c = 0; c < S && c < n_chunks; ++c) issue(c);
     }
     op.reset();
+    if constexpr (OpEdges<Op>::value) op.edges(left_edge, right_edge, xr, lane);
 
     for (int c = 0; c < n_chunks; ++c) {
       const uint32_t st = (uint32_t)(c % S);
@@ -204,7 +248,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
       if (lane == 0 && c >= 1 && c - 1 + S < n_chunks) issue(c - 1 + S);
 
       // ---- rows of this chunk ----
-      if (fast_strip && c * R + R <= n_feed) {
+      if (!OpSinglePath<Op>::value && fast_strip && c * R + R <= n_feed) {
         // whole chunk of an aligned, non-ragged strip: every row is fed; every row emits except the
         // first 2*HV rows of the band (chunk 0), which only fill the window.  No per-row tests.
         // The body is unrolled Op::UNROLL rows (the op's window period) and looped R/UNROLL times:
@@ -298,11 +342,12 @@ static inline bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) 
 // tens of MB (TLB reach, L2-resident halo rows) instead of hundreds.  36 rows (40 fed rows =
 // 5 chunks of R) measured best for the 5x5 Gaussian: 8.04 us per 4K frame vs 8.64 at 60 rows
 // and 10.9 at 244.  Tiny jobs use shorter bands to occupy more warps.
-static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv, int nw = kNW) {
+static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int strips, int n, int hv, int nw = kNW,
+                                 int dflt = 0) {
   int64_t forced = opt_get(optname, 0);
   if (forced > 0) return (int)forced;
   const long long warps = (long long)ctx_sm_count(c) * nw;
-  int br = 5 * kR - 2 * hv;
+  int br = dflt > 0 ? dflt : 5 * kR - 2 * hv;
   const long long items = (long long)strips * n * ((rows + br - 1) / br);
   if (items < warps) br = 4 * kR - 2 * hv;
   return br;
@@ -335,7 +380,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   }
   p.row_bytes = (int)src.v.row_bytes();
   p.strips = ceil_div(p.row_bytes, kOutBytes);
-  p.band_rows = pick_band_rows(c, band_opt, p.row_end - p.row_begin, p.strips, src.n, Op::HV, NW);
+  p.band_rows = pick_band_rows(c, band_opt, p.row_end - p.row_begin, p.strips, src.n, Op::HV, NW, OpBandRows<Op>::value);
   p.bands = ceil_div(p.row_end - p.row_begin, p.band_rows);
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;

@@ -189,6 +189,13 @@ def yuyv_to_sobel_mag_batch(srcs, mags) -> None:
     F.check(F.lib.rcv_yuyv_to_sobel_mag_batch(sa, da, n))
 
 
+def yuyv_to_bgr_gaussian5_batch(srcs, dsts) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_yuyv_to_bgr_gaussian5_batch(sa, da, n))
+
+
 # ---- runtime knobs ---------------------------------------------------------------------------
 def set_option(name: str, value: int) -> None:
     F.check(F.lib.rcv_set_option(name.encode(), value))

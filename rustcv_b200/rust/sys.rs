@@ -79,6 +79,7 @@ extern "C" {
 
     pub fn rcv_yuyv_to_bgr_gaussian5(src_yuyv: *const RcvMat, dst_bgr: *mut RcvMat) -> c_int;
     pub fn rcv_yuyv_to_sobel_mag(src_yuyv: *const RcvMat, mag_f32: *mut RcvMat) -> c_int;
+    pub fn rcv_yuyv_to_bgr_gaussian5_batch(srcs_yuyv: *const RcvMat, dsts_bgr: *mut RcvMat, n: i32) -> c_int;
     pub fn rcv_yuyv_to_sobel_mag_batch(srcs_yuyv: *const RcvMat, mags_f32: *mut RcvMat, n: i32) -> c_int;
 
     pub fn rcv_gaussian_blur_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, kw: i32, kh: i32, sigma_x: f64, sigma_y: f64) -> c_int;

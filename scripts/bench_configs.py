@@ -37,6 +37,8 @@ R.imgproc.init(LOCAL)
 stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(LOCAL), device=torch.device("cuda", LOCAL))
 R.imgproc.set_blocking(False)
 CPU = os.environ.get("CPU", "0") == "1" and WORLD == 1
+for kv in filter(None, os.environ.get("OPT", "").split(",")):  # OPT=name:value,name:value sets library options
+    R.imgproc.set_option(kv.split(":")[0], int(kv.split(":")[1]))
 
 
 def cpu_time(fn, reps):
@@ -187,6 +189,28 @@ def chain(n=32):
     src.free(); dst.free()
 
 
+def chain_gauss(n=32):
+    """raw 4K YUYV frame -> BGR -> GaussianBlur 5x5.  Fused kernel (5 B/px) against the
+    library's two stand-alone kernels (YUYV2BGR 5 B/px + GaussianBlur 6 B/px = 11 B/px)."""
+    h, w = 2160, 3840
+    src, dst = R.Mat.device_batch(n, h, w, 2), R.Mat.device_batch(n, h, w, 3)
+    base = O.fill_u8(7, h * w * 2)
+    fill_batch(src, lambda i: np.roll(base, i * 31).reshape(h, w, 2))
+    ms = timeit(lambda: R.imgproc.yuyv_to_bgr_gaussian5_batch(src, dst))
+    O.set_threads(8)
+    want = O.gaussian_blur(O.yuyv_to_bgr(base.reshape(h, w, 2)), (5, 5))
+    O.set_threads(1)
+    ok = bool((dst[0].to_numpy() == want).all())
+    R.imgproc.set_option("yuyvgauss.force_chain", 1)
+    ms_chain = timeit(lambda: R.imgproc.yuyv_to_bgr_gaussian5_batch(src, dst))
+    R.imgproc.set_option("yuyvgauss.force_chain", 0)
+    ok_chain = bool((dst[0].to_numpy() == want).all())
+    report(f"chain YUYV->BGR->GaussianBlur5x5 3840x2160 x{n}, fused kernel", ms, n * h * w, 5,
+           {"parity_frame0": ok, "unfused_2_kernel_chain_ms": ms_chain, "unfused_parity_frame0": ok_chain,
+            "speedup_vs_unfused": ms_chain / ms})
+    src.free(); dst.free()
+
+
 def cfg5sweep(n=8):
     """warpAffine tile height sweep (warp.tile_rows = 32 / 48 / 64 / automatic), parity of frame 0 each time."""
     s = 4096
@@ -219,7 +243,7 @@ def cfg5sweep(n=8):
     src.free(); dst.free(); src8.free(); dst8.free()
 
 
-ALL = {"chain": chain, "cfg5sweep": cfg5sweep, "cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
+ALL = {"chain": chain, "chain_gauss": chain_gauss, "cfg5sweep": cfg5sweep, "cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
        "cfg4full": lambda: cfg4(256), "cfg5full": lambda: cfg5(64)}
 for name in (sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]):
     ALL[name]()

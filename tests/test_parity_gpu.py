@@ -1152,3 +1152,80 @@ def test_banded_pipeline_fallback_and_mixed_locations(small_bands, oracle):
     R.imgproc.gaussian_blur(R.Mat.from_numpy(bgr), hp, (5, 5), 0.0)
     assert R.imgproc.launch_count() - n0 == 1
     assert_same(hp.to_numpy(), want, "pageable")
+
+
+# ---- fused YUYV -> BGR -> GaussianBlur 5x5 (one kernel) ------------------------------------------------
+def _yuyv_gauss_oracle(oracle, yuyv):
+    return oracle.gaussian_blur(oracle.yuyv_to_bgr(yuyv), (5, 5))
+
+
+# widths chosen so the row ends at every macro-pixel phase of a lane (m = 0..3), exactly on a lane boundary,
+# exactly on a strip boundary (240 px), one macro-pixel into the next strip, and inside the left-edge lane
+YG_SHAPES = [(40, 8), (40, 10), (40, 12), (40, 14), (40, 16), (33, 238), (33, 240), (33, 242), (33, 244), (33, 246),
+             (33, 248), (9, 480), (17, 482), (270, 480), (64, 1000), (480, 640), (11, 722)]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+@pytest.mark.parametrize("shape", YG_SHAPES)
+def test_yuyv_to_bgr_gaussian5_fused(rcv, oracle, where, shape):
+    R = rcv
+    h, w = shape
+    yuyv = oracle.fill_u8(700 + h + w, h * w * 2).reshape(h, w, 2)
+    s = mats(R, yuyv, where)
+    d = out_like(R, s, where, channels=3)
+    n0 = R.imgproc.launch_count()
+    R.imgproc.yuyv_to_bgr_gaussian5(s, d)
+    assert R.imgproc.launch_count() - n0 == 1, "one fused kernel"
+    assert_same(d.to_numpy(), _yuyv_gauss_oracle(oracle, yuyv), f"yuyv->bgr->gauss5 fused {shape} {where}")
+
+
+def test_yuyv_to_bgr_gaussian5_chain_batch_bands(rcv, oracle):
+    """The fused kernel equals the library's two stand-alone kernels (forced), on batches, across internal band
+    seams, with saturated inputs, and on tiny / odd-width images that take the two-kernel path by themselves."""
+    R = rcv
+    h, w = 211, 1202
+    yuyv = oracle.fill_u8(78, h * w * 2).reshape(h, w, 2)
+    yuyv[50:90, 300:700] = 255
+    yuyv[100:140, 0:64] = 0
+    want = _yuyv_gauss_oracle(oracle, yuyv)
+    s = R.Mat.from_numpy(yuyv).upload()
+    for br in (0, 8, 12, 36, 100):
+        R.imgproc.set_option("yuyvgauss.band_rows", br)
+        d = s.like(channels=3)
+        R.imgproc.yuyv_to_bgr_gaussian5(s, d)
+        assert_same(d.to_numpy(), want, f"fused, band_rows {br}")
+    R.imgproc.set_option("yuyvgauss.band_rows", 0)
+    R.imgproc.set_option("yuyvgauss.force_chain", 1)
+    try:
+        d = s.like(channels=3)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.yuyv_to_bgr_gaussian5(s, d)
+        assert R.imgproc.launch_count() - n0 == 2
+        assert_same(d.to_numpy(), want, "forced two-kernel chain")
+    finally:
+        R.imgproc.set_option("yuyvgauss.force_chain", 0)
+    for shape in ((5, 6), (7, 30), (12, 33)):
+        y2 = oracle.fill_u8(79, shape[0] * shape[1] * 2).reshape(shape[0], shape[1], 2)
+        d = R.Mat.empty()
+        R.imgproc.yuyv_to_bgr_gaussian5(R.Mat.from_numpy(y2), d)
+        got, ref = d.to_numpy(), _yuyv_gauss_oracle(oracle, y2)
+        if shape[1] & 1:  # the conversion leaves the odd last pixel untouched (videoio/mod.rs:350): compare the rest
+            got, ref = got[:, :shape[1] - 3], ref[:, :shape[1] - 3]
+        assert_same(got, ref, f"small {shape}")
+    n, hh, ww = 4, 96, 720
+    frames = [oracle.fill_u8(800 + j, hh * ww * 2).reshape(hh, ww, 2) for j in range(n)]
+    src = R.Mat.device_batch(n, hh, ww, 2)
+    dst = R.Mat.device_batch(n, hh, ww, 3)
+    for j in range(n):
+        upload_into(R, frames[j], src[j])
+    n0 = R.imgproc.launch_count()
+    R.imgproc.yuyv_to_bgr_gaussian5_batch(src, dst)
+    assert R.imgproc.launch_count() - n0 == 1
+    for j in range(n):
+        assert_same(dst[j].to_numpy(), _yuyv_gauss_oracle(oracle, frames[j]), f"batch frame {j}")
+    src.free(); dst.free()
+    hs = [mats(R, f, "pinned") for f in frames]
+    hd = [m.like(channels=3) for m in hs]
+    R.imgproc.yuyv_to_bgr_gaussian5_batch(hs, hd)
+    for j in range(n):
+        assert_same(hd[j].to_numpy(), _yuyv_gauss_oracle(oracle, frames[j]), f"pinned batch frame {j}")
