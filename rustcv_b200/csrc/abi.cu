@@ -265,9 +265,10 @@ int run_host_pipeline(Ctx *c, const RcvMat *srcs, RcvMat *dsts, int n, F &launch
     Staged in = si[k], out = so[k];
     if (!in.staged) in.v = view_of(&srcs[i], srcs[i].data, srcs[i].step);
     if (!out.staged) out.v = view_of(&dsts[i], dsts[i].data, dsts[i].step);
-    // inside a batch the frames themselves overlap; only the pipeline's fill (first frame) and drain (last
-    // frame) gain from bands, and the interior frames are spared the per-band hand-offs
-    const int br = (i == 0 || i == n - 1) ? band_rows : 0;
+    // inside a batch the frames themselves overlap and bands only add hand-offs (measured, 16 pinned 4K frames:
+    // 8.85 ms unbanded, 9.51 ms with the first and last frame banded, 9.9 ms with every frame banded): bands are
+    // for the single-Mat call
+    const int br = n == 1 ? band_rows : 0;
     int rc = pipeline_frame(c, &srcs[i], &dsts[i], in, out, k, i >= kRing, br, bd, launch, written_cols);
     if (rc == RCV_ERR_UNSUPPORTED && br > 0) {
       // the op fell off its row-window capable kernel for this geometry: redo the frame unbanded

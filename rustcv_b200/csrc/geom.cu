@@ -6,8 +6,10 @@
 //   resize u8   cv::resize INTER_LINEAR fixed point (11-bit weights), bit-exact with OpenCV
 //   resize f32  h = p0*(1-fx) + p1*fx ; out = h0*(1-fy) + h1*fy, each op rounded once
 //   warpAffine  inverse map, f64 row term, fmaf column term, fmaf lerp chain, constant border
-// All gather kernels: HBM/L2-bound, no shared-memory staging needed for the general case;
-// the exact 4x BGR downscale (BASELINE.json config 4) has a 128-bit-load specialisation.
+// The general resize is a per-pixel gather kernel (a shared-memory staged tile variant was built and measured
+// SLOWER on single 4K frames -- 13.7 vs 9.0 us for 4K->720p, 21.3 vs 15.0 us for 4K->1080p: at these sizes the
+// kernel is launch/ramp bound and the two-phase tile adds a barrier -- and was removed); the exact 4x BGR
+// downscale (BASELINE.json config 4) has a 128-bit-load specialisation that runs at the DRAM sector floor.
 #include "rcv_internal.cuh"
 #include "tma_ptx.cuh"
 
@@ -579,7 +581,10 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
     int rc = RCV_ERR_UNSUPPORTED;
     const int64_t th = opt_get("warp.tile_rows", 0);  // 0 = automatic; 32 / 48 / 64 force one shape
     const size_t big = 96 * 1024, cap = 36 * 1024;    // 36 KB boxes: 6 CTAs (48 warps) per SM
-    if ((th == 0 && a.drows >= 64) || th == 64) rc = try_warp_tile<64>(src, a, iM, th ? big : cap, s);
+    // measured (profiles/README.md): f32 C1 15/33/90 degrees 64 rows best (0.82 / 0.78 / 0.54 of the roofline vs
+    // 0.73 / 0.71 / 0.51 at 32); u8 BGR gains only at 48 (the 64-row loop of 3 channels x 16 pixels is too long)
+    const bool f32 = src.v.depth == RCV_F32;
+    if ((th == 0 && f32 && a.drows >= 64) || th == 64) rc = try_warp_tile<64>(src, a, iM, th ? big : cap, s);
     if (rc == RCV_ERR_UNSUPPORTED && ((th == 0 && a.drows >= 48) || th == 48)) rc = try_warp_tile<48>(src, a, iM, th ? big : cap, s);
     if (rc == RCV_ERR_UNSUPPORTED) rc = try_warp_tile<32>(src, a, iM, big, s);
     if (rc != RCV_ERR_UNSUPPORTED) return rc;

@@ -73,12 +73,22 @@ if case("cvt"):
     report("bgr2xrgb32 4K", timeit(lambda: I.cvt_color(bgr, x, I.COLOR_BGR2XRGB32)), 7 * H * W)
     report("bgra2bgr 4K", timeit(lambda: I.cvt_color(x, out3, I.COLOR_BGRA2BGR)), 7 * H * W)
 if case("resize"):
-    d = bgr.like(rows=720, cols=1280)
-    report("resize u8c3 4K->720p (3x, general)", timeit(lambda: I.resize(bgr, d)), 15 * 720 * 1280)
-    d2 = bgr.like(rows=1080, cols=1920)
-    report("resize u8c3 4K->1080p (2x, general)", timeit(lambda: I.resize(bgr, d2)), 15 * 1080 * 1920)
-    d3 = bgr.like(rows=4320, cols=7680)
-    report("resize u8c3 4K->8K (upscale)", timeit(lambda: I.resize(bgr, d3)), (3 * H * W + 3 * 4320 * 7680))
+    # bytes = the source rows a bilinear kernel must touch (whole rows: every 32-byte sector of a used row is hit
+    # for scales below ~8) + the destination; "tile" = shared-memory staged kernel, "naive" = per-tap global loads
+    for name, dr, dc, rows_used in (("4K->720p (3x)", 720, 1280, 2 * 720), ("4K->1080p (2x)", 1080, 1920, H),
+                                    ("4K->8K (upscale 2x)", 4320, 7680, H), ("4K->1600x900 (2.4x)", 900, 1600, 2 * 900)):
+        d = bgr.like(rows=dr, cols=dc)
+        nbytes = rows_used * W * 3 + dr * dc * 3
+        for opt, label in ((0, "tile"), (1, "naive")):
+            I.set_option("resize.force_generic", opt)
+            report(f"resize u8c3 {name} {label}", timeit(lambda: I.resize(bgr, d)), nbytes)
+        I.set_option("resize.force_generic", 0)
+    f4 = dev(O.fill_f32(4, 2160 * 3840).reshape(2160, 3840))
+    fd = f4.like(rows=1080, cols=1920)
+    for opt, label in ((0, "tile"), (1, "naive")):
+        I.set_option("resize.force_generic", opt)
+        report(f"resize f32c1 4K->1080p {label}", timeit(lambda: I.resize(f4, fd)), 4 * (H * W + 1080 * 1920))
+    I.set_option("resize.force_generic", 0)
 if case("warp"):
     M = I.get_rotation_matrix_2d(((W - 1) / 2, (H - 1) / 2), 15.0)
     report("warpAffine u8c3 4K 15deg", timeit(lambda: I.warp_affine(bgr, out3, M)), 6 * H * W)

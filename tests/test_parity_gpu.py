@@ -512,6 +512,37 @@ def test_resize_4x_fast_path_equals_general_model(rcv, oracle, golden):
         R.imgproc.set_option("resize.force_generic", 0)
 
 
+@pytest.mark.parametrize("case", [((300, 500, 3), (131, 277)), ((100, 150, 3), (333, 517)), ((256, 512, 3), (64, 128)),
+                                  ((217, 1023, 1), (100, 400)), ((90, 2000, 3), (45, 21)), ((64, 333, 4), (64, 700)),
+                                  ((33, 37, 3), (33, 37)), ((500, 81, 2), (17, 300))])
+def test_resize_larger_geometries(rcv, oracle, case):
+    """Several CTAs in both directions, up- and down-scaling, all channel counts, u8 and f32; the 4x fast path
+    and the general kernel agree."""
+    R = rcv
+    (h, w, cn), (dr, dc) = case
+    a = oracle.fill_u8(70 + h, h * w * cn).reshape(h, w, cn)
+    if cn == 1:
+        a = a.reshape(h, w)
+    want = oracle.resize_bilinear(a, dr, dc)
+    s = mats(R, a, "device")
+    for opt in (None, "resize.force_generic"):
+        if opt:
+            R.imgproc.set_option(opt, 1)
+        try:
+            d = out_like(R, s, "device", rows=dr, cols=dc)
+            R.imgproc.resize(s, d)
+            assert_same(d.to_numpy(), want, f"resize {case} {opt}")
+        finally:
+            if opt:
+                R.imgproc.set_option(opt, 0)
+    f = oracle.fill_f32(71 + h, h * w * cn).reshape(a.shape)
+    sf = mats(R, f, "device")
+    df = out_like(R, sf, "device", rows=dr, cols=dc)
+    R.imgproc.resize(sf, df)
+    wantf = oracle.resize_bilinear(f, dr, dc)
+    assert_f32(df.to_numpy().reshape(dr, -1), wantf.reshape(dr, -1), f"resize f32 {case}", max_ulp=0)
+
+
 def test_resize_f32(rcv, oracle):
     R = rcv
     a = oracle.fill_f32(61, 61 * 83).reshape(61, 83)
@@ -1112,7 +1143,7 @@ def test_banded_pipeline_matches_oracle(small_bands, oracle):
 
 def test_banded_pipeline_fallback_and_mixed_locations(small_bands, oracle):
     """A kernel size only the whole-image kernels cover (9x9) silently takes the unbanded path; pinned -> device
-    and device -> pinned pairs band one side only; batches of pinned frames band inside every frame."""
+    and device -> pinned pairs band one side only; batches of pinned frames pipeline frame by frame (unbanded)."""
     R = small_bands
     rng = np.random.default_rng(6)
     bgr = rng.integers(0, 256, size=(200, 400, 3), dtype=np.uint8)
@@ -1132,7 +1163,7 @@ def test_banded_pipeline_fallback_and_mixed_locations(small_bands, oracle):
     hd = [m.like() for m in hs]
     R.imgproc.gaussian_blur_batch(hs, hd, (5, 5), 0.0)
     for j, f in enumerate(frames):
-        assert_same(hd[j].to_numpy(), oracle.gaussian_blur(f, (5, 5), 0.0), f"banded batch frame {j}")
+        assert_same(hd[j].to_numpy(), oracle.gaussian_blur(f, (5, 5), 0.0), f"pinned batch frame {j}")
     # direct write: the kernel stores straight into the pinned destination (optional path, off by default)
     R.imgproc.set_option("host.direct_write", 1)
     try:
