@@ -43,11 +43,29 @@ struct CvtArgs {
   size_t dstep, dfs;
   int rows, cols;
   int per_row;  // work items (threads) per row
+  int mode;     // how threads map to (row, item): see cvt_index
+  int rpb;      // mode 1: rows per block
+  int magic;    // mode 1: ceil(2^16 / per_row)
 };
 
-// Threads are numbered over (row, item) so narrow images still fill whole CTAs
-// (a 640-wide YUYV row is only 40 vector items); frames of a batch are blockIdx.y.
+// Thread -> (row, item).  Frames of a batch are blockIdx.y in every mode.
+//   mode 1  narrow rows (per_row <= blockDim.x; a 640-wide YUYV row is only 40 vector items): a block takes
+//           rpb = blockDim.x / per_row whole rows; row-in-block = (t * magic) >> 16, exact for t < 512
+//   mode 2  wide rows: blockIdx.x walks the items of a row, blockIdx.z is the row (rows <= 65535)
+//   mode 0  anything else: threads numbered over (row, item) with a 64-bit division
+// (the division of mode 0 was a quarter of the YUYV->BGR kernel's instructions)
 __device__ __forceinline__ bool cvt_index(const CvtArgs &a, int &r, int &i) {
+  if (a.mode == 1) {
+    const int t = (int)threadIdx.x, lr = (t * a.magic) >> 16;
+    i = t - lr * a.per_row;
+    r = (int)blockIdx.x * a.rpb + lr;
+    return lr < a.rpb && r < a.rows;
+  }
+  if (a.mode == 2) {
+    i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    r = (int)blockIdx.z;
+    return i < a.per_row;
+  }
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)a.rows * a.per_row) return false;
   r = (int)(t / a.per_row);
@@ -100,8 +118,6 @@ __global__ void __launch_bounds__(256) k_cvt_scalar(CvtArgs a) {
 // byte k of a little-endian word array
 __device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu; }
 
-// {lo16(a), lo16(b)} as one register
-__device__ __forceinline__ uint32_t pair16(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }
 
 // YUYV/UYVY -> BGR: a thread converts 8 macro-pixels: 32 B in (2 x LDG.128) -> 48 B out (3 x STG.128).
 // -> GRAY: 16 px -> 16 B out.
@@ -135,13 +151,15 @@ __global__ void __launch_bounds__(128) k_yuv422_vec(CvtArgs a) {
       uint32_t out[12];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // two macro-pixels -> 12 bytes = 3 words
-        Px6 a0 = yuv_word<CODE == RCV_COLOR_UYVY2BGR>(in[2 * k]);
-        Px6 a1 = yuv_word<CODE == RCV_COLOR_UYVY2BGR>(in[2 * k + 1]);
-        uint32_t p0 = pair16(a0.b0, a0.g0), p1 = pair16(a0.r0, a0.b1), p2 = pair16(a0.g1, a0.r1);
-        uint32_t p3 = pair16(a1.b0, a1.g0), p4 = pair16(a1.r0, a1.b1), p5 = pair16(a1.g1, a1.r1);
-        out[3 * k] = __byte_perm(p0, p1, 0x7531);      // B0 G0 R0 B1
-        out[3 * k + 1] = __byte_perm(p2, p3, 0x7531);  // G1 R1 B0' G0'
-        out[3 * k + 2] = __byte_perm(p4, p5, 0x7531);  // R0' B1' G1' R1'
+        constexpr bool U = CODE == RCV_COLOR_UYVY2BGR;
+        uint32_t b0, g0, r0, b1, g1, r1;  // (pixel 0, pixel 1) of each channel as 16-bit lanes, values 0..255
+        yuv_word_pairs<U>(in[2 * k], b0, g0, r0);
+        yuv_word_pairs<U>(in[2 * k + 1], b1, g1, r1);
+        const uint32_t X = __byte_perm(g0, r0, 0x6240);    // G0 R0 G1 R1
+        const uint32_t Y = __byte_perm(b1, g1, 0x6240);    // B0' G0' B1' G1'
+        out[3 * k] = __byte_perm(b0, X, 0x2540);           // B0 G0 R0 B1
+        out[3 * k + 1] = __byte_perm(X, Y, 0x5432);        // G1 R1 B0' G0'
+        out[3 * k + 2] = __byte_perm(r1, Y, 0x2760);       // R0' B1' G1' R1'
       }
       uint4 *dp = (uint4 *)(d + (size_t)g * 48);
       dp[0] = make_uint4(out[0], out[1], out[2], out[3]);
@@ -285,7 +303,7 @@ static bool aligned16(const DBatch &b) {
 
 template <int CODE>
 static int launch_code(const DBatch &src, const DBatch &dst, cudaStream_t s) {
-  CvtArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows, src.v.cols, 0};
+  CvtArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows, src.v.cols, 0, 0, 0, 0};
   bool vec = aligned16(src) && aligned16(dst);
   constexpr bool yuv = (CODE == RCV_COLOR_YUYV2BGR || CODE == RCV_COLOR_UYVY2BGR || CODE == RCV_COLOR_YUYV2GRAY);
   const int threads = vec ? 128 : 256;
@@ -294,10 +312,22 @@ static int launch_code(const DBatch &src, const DBatch &dst, cudaStream_t s) {
   else
     a.per_row = yuv ? src.v.cols / 2 : src.v.cols;
   if (a.per_row == 0) return RCV_OK;
-  const long long total = (long long)a.rows * a.per_row;
-  const long long blocks = (total + threads - 1) / threads;
-  if (blocks > 0x7fffffffLL) return fail(RCV_ERR_UNSUPPORTED, "image too large");
-  dim3 grid((unsigned)blocks, src.n, 1);
+  dim3 grid;
+  if (a.per_row <= threads) {
+    a.mode = 1;
+    a.rpb = threads / a.per_row;
+    a.magic = (65536 + a.per_row - 1) / a.per_row;
+    grid = dim3((unsigned)ceil_div(a.rows, a.rpb), src.n, 1);
+  } else if (a.rows <= 65535) {
+    a.mode = 2;
+    grid = dim3((unsigned)ceil_div(a.per_row, threads), src.n, (unsigned)a.rows);
+  } else {
+    a.mode = 0;
+    const long long total = (long long)a.rows * a.per_row;
+    const long long blocks = (total + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return fail(RCV_ERR_UNSUPPORTED, "image too large");
+    grid = dim3((unsigned)blocks, src.n, 1);
+  }
   if (vec) {
     if constexpr (yuv)
       k_yuv422_vec<CODE><<<grid, threads, 0, s>>>(a);

@@ -66,12 +66,7 @@ struct YuyvGauss5Op {
   static __device__ __forceinline__ void convert(const uint4 &q, uint32_t (&o)[12]) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const Px6 p = yuv_word<false>(w[k]);  // channel value = byte 1 of each (clamped to 0..65535)
-      o[3 * k + 0] = __byte_perm(p.b0, p.b1, 0x6521);
-      o[3 * k + 1] = __byte_perm(p.g0, p.g1, 0x6521);
-      o[3 * k + 2] = __byte_perm(p.r0, p.r1, 0x6521);
-    }
+    for (int k = 0; k < 4; ++k) yuv_word_pairs<false>(w[k], o[3 * k + 0], o[3 * k + 1], o[3 * k + 2]);
   }
 
   template <int J8>
