@@ -98,6 +98,22 @@ int main(int argc, char **argv) {
     EXPECT(imgproc::cvt_color(img, gray, imgproc::COLOR_BGR2GRAY).is_ok());
     EXPECT(gray.data == wgray.data);
   }
+  // fused decode -> process chain: raw YUYV -> BGR -> Gray -> f32 -> Sobel magnitude in one kernel, against the
+  // oracle's stand-alone stages run one after the other
+  {
+    const int h = 120, w = 480;
+    core::Mat yuyv = core::Mat::create(h, w, 2), mag;
+    orc_fill_u8(21, yuyv.data.data(), yuyv.data.size());
+    core::Mat bgr = core::Mat::create(h, w, 3), gray = core::Mat::create(h, w, 1);
+    core::Mat gf = core::Mat::create(h, w, 1, core::F32), want = core::Mat::create(h, w, 1, core::F32);
+    orc_yuyv_to_bgr_strided(yuyv.data.data(), yuyv.step, bgr.data.data(), bgr.step, h, w);
+    orc_bgr_to_gray_strided(bgr.data.data(), bgr.step, gray.data.data(), gray.step, h, w);
+    orc_convert_to(gray.data.data(), gray.step, 0, gf.data.data(), gf.step, 1, h, w, 1.0, 0.0);
+    orc_sobel3_f32((const float *)gf.data.data(), gf.step, nullptr, 0, nullptr, 0, (float *)want.data.data(), want.step, h, w);
+    EXPECT(imgproc::yuyv_to_sobel_magnitude(yuyv, mag).is_ok());
+    EXPECT(mag.rows == h && mag.cols == w && mag.channels == 1 && mag.depth == core::F32);
+    EXPECT(mag.data == want.data);
+  }
   std::puts("host_mirror ok");
   return 0;
 }
