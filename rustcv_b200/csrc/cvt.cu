@@ -430,12 +430,48 @@ int launch_convert(Ctx *, const DBatch &src, const DBatch &dst, double alpha, do
   return RCV_OK;
 }
 
+// NV12 vector kernel: a thread converts 16 pixels of one row -- 16 B of Y, the 16 B (8 U,V pairs) of the chroma
+// row r/2 under them, 48 B out.  One PRMT interleaves (Y0, U, Y1, V) into the word layout of a YUYV macro-pixel,
+// after which the arithmetic and the packing are k_yuv422_vec's.
+__global__ void __launch_bounds__(128) k_nv12_vec(Nv12Args a, int per_row) {
+  const int g = (int)(blockIdx.x * blockDim.x + threadIdx.x), r = (int)blockIdx.y;
+  if (g >= per_row) return;
+  const uint4 yq = __ldg((const uint4 *)(a.y + (size_t)r * a.ystep + (size_t)g * 16));
+  const uint4 cq = __ldg((const uint4 *)(a.uv + (size_t)(r >> 1) * a.uvstep + (size_t)g * 16));
+  const uint32_t yw[4] = {yq.x, yq.y, yq.z, yq.w}, cw[4] = {cq.x, cq.y, cq.z, cq.w};
+  uint32_t out[12];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // 4 pixels = 2 macro-pixels -> 12 bytes
+    const uint32_t m0 = __byte_perm(yw[k], cw[k], 0x5140);  // Y0 U0 Y1 V0
+    const uint32_t m1 = __byte_perm(yw[k], cw[k], 0x7362);  // Y2 U1 Y3 V1
+    uint32_t b0, g0, r0, b1, g1, r1;
+    yuv_word_pairs<false>(m0, b0, g0, r0);
+    yuv_word_pairs<false>(m1, b1, g1, r1);
+    const uint32_t X = __byte_perm(g0, r0, 0x6240);
+    const uint32_t Y = __byte_perm(b1, g1, 0x6240);
+    out[3 * k] = __byte_perm(b0, X, 0x2540);
+    out[3 * k + 1] = __byte_perm(X, Y, 0x5432);
+    out[3 * k + 2] = __byte_perm(r1, Y, 0x2760);
+  }
+  uint4 *dp = (uint4 *)(a.dst + (size_t)r * a.dstep + (size_t)g * 48);
+  dp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  dp[2] = make_uint4(out[8], out[9], out[10], out[11]);
+}
+
 int launch_nv12(Ctx *, const DView &y, const DView &uv, const DView &dst, cudaStream_t s) {
   if (y.rows > 65535) return fail(RCV_ERR_UNSUPPORTED, "rows > 65535");
   if (y.rows == 0 || y.cols == 0) return RCV_OK;
   Nv12Args a{y.data, y.step, uv.data, uv.step, dst.data, dst.step, y.rows, y.cols};
-  dim3 grid(ceil_div(ceil_div(y.cols, 2), 256), y.rows, 1);
-  k_nv12<<<grid, 256, 0, s>>>(a);
+  const bool al = ((((uintptr_t)y.data | y.step | (uintptr_t)uv.data | uv.step | (uintptr_t)dst.data | dst.step) & 15) == 0);
+  if (al && (y.cols & 15) == 0) {
+    const int per_row = y.cols / 16;
+    dim3 grid(ceil_div(per_row, 128), y.rows, 1);
+    k_nv12_vec<<<grid, 128, 0, s>>>(a, per_row);
+  } else {
+    dim3 grid(ceil_div(ceil_div(y.cols, 2), 256), y.rows, 1);
+    k_nv12<<<grid, 256, 0, s>>>(a);
+  }
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;

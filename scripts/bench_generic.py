@@ -72,6 +72,15 @@ if case("cvt"):
     x = bgr.like(channels=4)
     report("bgr2xrgb32 4K", timeit(lambda: I.cvt_color(bgr, x, I.COLOR_BGR2XRGB32)), 7 * H * W)
     report("bgra2bgr 4K", timeit(lambda: I.cvt_color(x, out3, I.COLOR_BGRA2BGR)), 7 * H * W)
+if case("nv12"):
+    yb = R.Mat.device_batch(1, H, W, 1)
+    y = dev(O.fill_u8(8, H * W).reshape(H, W))
+    uv = dev(O.fill_u8(9, (H // 2) * (W // 2) * 2).reshape(H // 2, W // 2, 2))
+    report("nv12->bgr 4K (1 frame/launch)", timeit(lambda: I.nv12_to_bgr(y, uv, out3), steps=50), int(4.5 * H * W))
+    big = dev(O.fill_u8(8, 4 * H * W).reshape(4 * H, W))
+    buv = dev(O.fill_u8(9, 4 * (H // 2) * (W // 2) * 2).reshape(2 * H, W // 2, 2))
+    bout = big.like(channels=3)
+    report("nv12->bgr 3840x8640 (4 stacked 4K frames)", timeit(lambda: I.nv12_to_bgr(big, buv, bout), steps=20), int(4.5 * 4 * H * W))
 if case("resize"):
     # bytes = the source rows a bilinear kernel must touch (whole rows: every 32-byte sector of a used row is hit
     # for scales below ~8) + the destination; "tile" = shared-memory staged kernel, "naive" = per-tap global loads

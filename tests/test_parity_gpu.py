@@ -198,6 +198,15 @@ def test_nv12(rcv, oracle):
     d = R.Mat.empty()
     R.imgproc.nv12_to_bgr(R.Mat.from_numpy(y), R.Mat.from_numpy(uv), d)
     assert_same(d.to_numpy(), oracle.nv12_to_bgr(y, uv.reshape(h // 2, w)), "nv12")
+    # widths that are multiples of 16 on aligned storage take the vector kernel (16 pixels per thread)
+    for (h, w), where in (((48, 64), "device"), ((270, 480), "device"), ((34, 1600), "pinned"), ((480, 640), "host")):
+        y = oracle.fill_u8(26 + w, h * w).reshape(h, w)
+        y[0:4, 0:32] = 255  # saturating lumas with random chroma
+        uv = oracle.fill_u8(27 + w, (h // 2) * (w // 2) * 2).reshape(h // 2, w // 2, 2)
+        ym, um = mats(R, y, where), mats(R, uv, where)
+        d = out_like(R, ym, where, channels=3)
+        R.imgproc.nv12_to_bgr(ym, um, d)
+        assert_same(d.to_numpy(), oracle.nv12_to_bgr(y, uv.reshape(h // 2, w)), f"nv12 vec {h}x{w} {where}")
 
 
 # ---- GaussianBlur ---------------------------------------------------------------------------
