@@ -349,7 +349,16 @@ static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int stri
   const long long warps = (long long)ctx_sm_count(c) * nw;
   int br = dflt > 0 ? dflt : 5 * kR - 2 * hv;
   const long long items = (long long)strips * n * ((rows + br - 1) / br);
-  if (items < warps) br = 4 * kR - 2 * hv;
+  if (items < warps) {
+    // A job that fits one round (a single frame, a band of the host pipeline): its duration is the longest
+    // item, so cut the rows into as many bands as there are warps for this many strips -- one round, every warp
+    // busy, the shortest items that still are one round.  Measured on one 4K BGR frame: 14.6 us at 23 rows
+    // (2256 items for 2368 warps) vs 16.7 at 28 and 20.1 at 20 (two rounds).
+    const long long per = warps / ((long long)strips * n);  // bands available per strip column
+    long long b = per > 0 ? (rows + per - 1) / per : br;
+    if (b < 8) b = 8;
+    if (b < br) br = (int)b;
+  }
   return br;
 }
 

@@ -19,6 +19,8 @@ R.imgproc.init(0)
 stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(0))
 R.imgproc.set_blocking(False)
 I = R.imgproc
+for kv in filter(None, os.environ.get("OPT", "").split(",")):  # OPT=name:value,... sets library options
+    I.set_option(kv.split(":")[0], int(kv.split(":")[1]))
 
 
 def dev(a):
