@@ -142,6 +142,13 @@ RCV_API int rcv_bgra_to_bgr_packed(const uint8_t *src, size_t src_len, uint8_t *
  * rows x cols x 1, uv is rows/2 x cols/2 x 2. */
 RCV_API int rcv_nv12_to_bgr(const RcvMat *y, const RcvMat *uv, RcvMat *dst);
 
+/* The MJPEG branch of read(): header, then decompress to BGR at dst's pitch -- the two TurboJPEG calls of
+ * rustcv/src/videoio/mod.rs:205-232 (rustcv-camera/src/decode.rs:93-121), through nvJPEG.  dst is u8,
+ * channels = 3, rows x cols as reported by rcv_mjpeg_info; a device dst keeps the frame in HBM (only the
+ * compressed bytes cross PCIe).  Decoders differ in the last bits: parity with libjpeg-turbo is a tolerance. */
+RCV_API int rcv_mjpeg_info(const uint8_t *jpeg, size_t len, int32_t *width, int32_t *height);
+RCV_API int rcv_mjpeg_to_bgr(const uint8_t *jpeg, size_t len, RcvMat *dst);
+
 /* cv::Mat::convertTo between u8 and f32 Mats of one geometry (the seam between the u8 images the
  * reference's capture path produces and the f32 images Sobel / warpAffine take):
  * v = fmaf((float)src, (float)alpha, (float)beta); u8 results are saturate(rint(v)). */

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rcv_yuyv_to_bgr_packed": [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t],
     "rcv_bgra_to_bgr_packed": [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t],
     "rcv_nv12_to_bgr": [_MatP, _MatP, _MatP],
+    "rcv_mjpeg_info": [C.c_void_p, C.c_size_t, _P(C.c_int32), _P(C.c_int32)],
+    "rcv_mjpeg_to_bgr": [C.c_void_p, C.c_size_t, _MatP],
     "rcv_convert_to": [_MatP, _MatP, C.c_double, C.c_double],
     "rcv_gaussian_blur": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_double, C.c_double],
     "rcv_sep_filter2d": [_MatP, _MatP, _P(C.c_float), C.c_int32, _P(C.c_float), C.c_int32],

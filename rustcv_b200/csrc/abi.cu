@@ -812,4 +812,43 @@ int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs, RcvMat *mags, int32_t n) {
   }, -1, band_window(1));
 }
 
+// ---- MJPEG branch of read() (videoio/mod.rs:205-232) through nvJPEG ----------------------------------
+int rcv_mjpeg_info(const uint8_t *jpeg, size_t len, int32_t *width, int32_t *height) {
+  if (!jpeg || !width || !height) return fail(RCV_ERR_ARG, "NULL argument");
+  if (len < 4) return fail(RCV_ERR_SIZE, "JPEG buffer of %zu bytes", len);
+  Ctx *c = ctx_default();
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  RCV_CUDA(cudaSetDevice(c->device));
+  int w = 0, h = 0;
+  RCV_TRY(mjpeg_info(c, jpeg, len, &w, &h));
+  *width = w;
+  *height = h;
+  return RCV_OK;
+}
+
+int rcv_mjpeg_to_bgr(const uint8_t *jpeg, size_t len, RcvMat *dst) {
+  if (!jpeg) return fail(RCV_ERR_ARG, "jpeg is NULL");
+  if (len < 4) return fail(RCV_ERR_SIZE, "JPEG buffer of %zu bytes", len);
+  RCV_TRY(check_mat(dst, "dst"));
+  if (dst->depth != RCV_U8 || dst->channels != 3) return fail(RCV_ERR_DEPTH, "MJPEG decodes to u8 with channels = 3");
+  const RcvMat *mats[1] = {dst};
+  Ctx *c = pick_ctx(mats, 1);
+  if (!c) return RCV_ERR_NOT_INIT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  RCV_CUDA(cudaSetDevice(c->device));
+  int w = 0, h = 0;
+  RCV_TRY(mjpeg_info(c, jpeg, len, &w, &h));
+  if (w != dst->cols || h != dst->rows)
+    return fail(RCV_ERR_SIZE, "MJPEG frame is %dx%d, dst is %dx%d (the caller sizes dst: rcv_mjpeg_info)", w, h, dst->cols,
+                dst->rows);
+  if (w == 0 || h == 0) return RCV_OK;
+  Staged so;
+  RCV_TRY(stage_alloc(c, dst, SCR_STAGE_OUT0, &so));
+  RCV_TRY(launch_mjpeg(c, jpeg, len, so.v, c->stream));
+  RCV_TRY(copy_out(dst, so, c->stream));
+  if (ctx_blocking() || so.staged) RCV_CUDA(cudaStreamSynchronize(c->stream));
+  return RCV_OK;
+}
+
 }  // extern "C"

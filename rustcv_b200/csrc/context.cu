@@ -146,6 +146,7 @@ int rcv_shutdown(void) {
     if (!c) continue;
     cudaSetDevice(d);
     cudaStreamSynchronize(c->stream);
+    jpeg_destroy(c);
     for (int i = 0; i < SCR_COUNT; ++i)
       if (c->scratch[i]) cudaFree(c->scratch[i]);
     cudaStreamDestroy(c->stream);

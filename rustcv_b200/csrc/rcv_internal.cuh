@@ -7,6 +7,7 @@
 //   strip_*.cu   TMA strip-pipeline kernels (strip_pipeline.cuh): Gaussian u8, Sobel f32, filters, fused YUYV->Sobel
 //   filter.cu    generic separable / dense filters (u8 Q8, f32)
 //   geom.cu      bilinear resize, warpAffine
+//   mjpeg.cu     the MJPEG branch of read() through nvJPEG (library decoder)
 //   abi.cu       the extern "C" entry points of include/rcv_imgproc.h
 #pragma once
 
@@ -69,6 +70,7 @@ constexpr int kRing = 4;  // staging ring depth for host-resident batches
 enum ScratchSlot {
   SCR_STAGE_IN0 = 0,   // + slot            (kRing staged inputs; NV12 uses slot 1 for the UV plane)
   SCR_STAGE_OUT0 = 8,  // + slot*3 + output (kRing x up to 3 staged outputs)
+  SCR_JPEG_Y = 20,     // + plane: Y, Cb, Cr samples of the MJPEG branch (20..22)
   SCR_TABLE_X = 24,
   SCR_TABLE_Y = 25,
   SCR_TAPS = 26,
@@ -89,6 +91,7 @@ struct Ctx {
   size_t scratch_bytes[SCR_COUNT] = {};
   unsigned counter_parity = 0;       // which of the two strip-kernel work counters the next launch uses
   int resize_key[4] = {0, 0, 0, 0};  // geometry of the resize tables currently in SCR_TABLE_X/Y
+  void *jpeg = nullptr;              // nvJPEG handle + state of the MJPEG branch (mjpeg.cu), created on first use
   std::mutex mu;
 };
 
@@ -131,6 +134,10 @@ int launch_warp_affine(Ctx *c, const DBatch &src, const DBatch &dst, const doubl
                        cudaStream_t s);
 int launch_yuyv_gauss5(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
 int launch_yuyv_sobel(Ctx *c, const DBatch &src, const DBatch &mag, cudaStream_t s);
+// MJPEG branch (nvJPEG): header size, decode to BGR at dst.step, teardown
+int mjpeg_info(Ctx *c, const uint8_t *jpeg, size_t len, int *width, int *height);
+int launch_mjpeg(Ctx *c, const uint8_t *jpeg, size_t len, const DView &dst, cudaStream_t s);
+void jpeg_destroy(Ctx *c);
 
 // host-side helpers shared by abi.cu and the launchers (OpenCV models, see oracle/)
 int gaussian_ksize(double sigma, bool is_u8);

@@ -228,18 +228,20 @@ constexpr uint32_t BGRA = fourcc('B', 'G', 'R', 'A');
 constexpr uint32_t MJPEG = fourcc('M', 'J', 'P', 'G');
 
 // The conversion step of VideoCapture::read (videoio/mod.rs:181-260): size `mat`, branch on
-// FourCC, convert a PACKED frame.  Returns code RCV_ERR_UNSUPPORTED for MJPEG (out of scope).
+// FourCC, convert a PACKED frame.  MJPG frames are decoded by nvJPEG (header first, like TurboJPEG's read_header).
 inline Result decode_frame(const uint8_t *data, size_t len, uint32_t width, uint32_t height, uint32_t fcc,
                            core::Mat &mat) {
+  if (fcc == MJPEG) {  // videoio/mod.rs:205-232: the frame's own header gives the size
+    int32_t w = 0, h = 0;
+    Result r = check(rcv_mjpeg_info(data, len, &w, &h));
+    if (!r.is_ok()) return r;
+    mat.ensure_size(h, w, 3);
+    RcvMat d = mat.pod();
+    return check(rcv_mjpeg_to_bgr(data, len, &d));
+  }
   mat.ensure_size((int32_t)height, (int32_t)width, 3);
   if (fcc == YUYV) return check(rcv_yuyv_to_bgr_packed(data, len, mat.data.data(), mat.data.size(), width, height));
   if (fcc == BGRA) return check(rcv_bgra_to_bgr_packed(data, len, mat.data.data(), mat.data.size(), width, height));
-  if (fcc == MJPEG) {
-    Result r;
-    r.code = RCV_ERR_UNSUPPORTED;
-    r.message = "MJPEG decode is outside the per-pixel hot path";
-    return r;
-  }
   if (len == mat.data.size()) std::memcpy(mat.data.data(), data, len);  // "Assume RGB/BGR or copy" (:253-257)
   return Result();
 }
@@ -249,6 +251,7 @@ inline Result decode_frame(const uint8_t *data, size_t len, uint32_t width, uint
 // `mat` must already be height x width x 3.  stride = bytes between source rows (0 = packed).
 inline Result decode_frame(const uint8_t *data, size_t len, uint32_t width, uint32_t height, uint32_t fcc,
                            core::DeviceMat &mat, size_t stride = 0) {
+  if (fcc == MJPEG) return check(rcv_mjpeg_to_bgr(data, len, &mat.pod()));  // only the compressed frame crosses PCIe
   const int bpp = fcc == YUYV ? 2 : fcc == BGRA ? 4 : 0;
   Result r;
   if (!bpp) {

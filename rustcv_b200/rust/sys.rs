@@ -66,6 +66,9 @@ extern "C" {
     pub fn rcv_bgra_to_bgr_packed(src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, width: usize, height: usize) -> c_int;
     pub fn rcv_nv12_to_bgr(y: *const RcvMat, uv: *const RcvMat, dst: *mut RcvMat) -> c_int;
 
+    pub fn rcv_mjpeg_info(jpeg: *const u8, len: usize, width: *mut i32, height: *mut i32) -> c_int;
+    pub fn rcv_mjpeg_to_bgr(jpeg: *const u8, len: usize, dst: *mut RcvMat) -> c_int;
+
     pub fn rcv_convert_to(src: *const RcvMat, dst: *mut RcvMat, alpha: f64, beta: f64) -> c_int;
 
     pub fn rcv_gaussian_blur(src: *const RcvMat, dst: *mut RcvMat, kw: i32, kh: i32, sigma_x: f64, sigma_y: f64) -> c_int;

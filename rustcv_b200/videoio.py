@@ -1,8 +1,8 @@
 """The pixel-format dispatch of `VideoCapture::read` / `decode_frame`, on the GPU.
 
 Mirrors rustcv/src/videoio/mod.rs:181-260 (size the Mat, branch on FourCC, convert) and
-rustcv-camera/src/decode.rs:36-86.  Camera I/O itself (drivers, streams, MJPEG) is out
-of scope; this module is the step between a raw frame buffer and
+rustcv-camera/src/decode.rs:36-86.  Camera I/O itself (drivers, streams) is out
+of scope; this module is the step between a raw (or MJPG) frame buffer and
 a BGR `Mat`.
 """
 from __future__ import annotations
@@ -31,6 +31,14 @@ NV12 = fourcc("NV12")
 MJPEG = fourcc("MJPG")
 
 
+def mjpeg_info(data: np.ndarray) -> tuple[int, int]:
+    """(width, height) from the JPEG header (Decompressor::read_header, videoio/mod.rs:214-216)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    w, h = C.c_int32(0), C.c_int32(0)
+    F.check(F.lib.rcv_mjpeg_info(data.ctypes.data, data.size, C.byref(w), C.byref(h)))
+    return w.value, h.value
+
+
 def decode_frame(data: np.ndarray, width: int, height: int, fcc: int, mat: Mat, stride: int | None = None) -> bool:
     """Converts one raw frame into `mat` (BGR, 3 channels), sizing it like `read` does.
 
@@ -38,9 +46,16 @@ def decode_frame(data: np.ndarray, width: int, height: int, fcc: int, mat: Mat, 
     macro-pixels (videoio/mod.rs:203,344-371).  With `stride` the rows are `stride`
     bytes apart (Frame.stride, rustcv-core/src/frame.rs:20-22 -- populated by the
     backends and ignored by the reference's facade).
-    Returns False for formats this path does not convert (MJPEG: decode.rs:93-140).
+    MJPG frames (videoio/mod.rs:205-232) are decoded by nvJPEG straight to BGR at the Mat's pitch; width and
+    height come from the JPEG header, as in the reference.  Returns False for formats this path does not convert.
     """
     data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    if fcc == MJPEG:
+        w, h = mjpeg_info(data)
+        if mat.loc == F.RCV_HOST:
+            mat.ensure_size(h, w, 3, U8)
+        F.check(F.lib.rcv_mjpeg_to_bgr(data.ctypes.data, data.size, C.byref(mat.c())))
+        return True
     if mat.loc == F.RCV_HOST:
         mat.ensure_size(height, width, 3, U8)  # videoio/mod.rs:192-199
     elif (mat.rows, mat.cols, mat.channels) != (height, width, 3):

@@ -40,7 +40,8 @@ int main(int argc, char **argv) {
     for (uint8_t v : m.data) EXPECT(v < 10);
     // the facade silently returns on a short source (videoio/mod.rs:346-348); the ABI reports it
     EXPECT(videoio::decode_frame(white, 3, 2, 1, videoio::YUYV, m).code == RCV_ERR_SIZE);
-    EXPECT(videoio::decode_frame(white, 4, 2, 1, videoio::MJPEG, m).code == RCV_ERR_UNSUPPORTED);
+    // MJPG frames go to nvJPEG: four bytes of YUYV are not a JPEG
+    EXPECT(videoio::decode_frame(white, 4, 2, 1, videoio::MJPEG, m).code == RCV_ERR_ARG);
   }
   // config 1: SplitMix64 seed 1, 640x480
   {

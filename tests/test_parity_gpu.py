@@ -1269,3 +1269,58 @@ def test_yuyv_to_bgr_gaussian5_chain_batch_bands(rcv, oracle):
     R.imgproc.yuyv_to_bgr_gaussian5_batch(hs, hd)
     for j in range(n):
         assert_same(hd[j].to_numpy(), _yuyv_gauss_oracle(oracle, frames[j]), f"pinned batch frame {j}")
+
+
+# ---- MJPEG branch of read() through nvJPEG ------------------------------------------------------------
+def test_mjpeg_decode_matches_libjpeg_turbo_within_tolerance(rcv):
+    """rcv_mjpeg_to_bgr (nvJPEG entropy decode + IDCT, then this repo's libjpeg-style fancy upsampling and colour
+    conversion kernel) against cv2.imdecode (libjpeg-turbo, the reference's decoder family) on the committed JPEG
+    frames: 4:4:4, 4:2:0, 4:2:2, odd sizes, grayscale.  Decoders differ in the IDCT's last bit, so this is a
+    tolerance, not bit-exactness: every sample within 4 levels, mean absolute difference below 0.1 (measured:
+    max 3, mean 0.013-0.035: about 3 % of the samples are off by one).  With nvJPEG's own colour path (option
+    mjpeg.library_color) the same frames differ by a mean of 0.5 (4:4:4) to 2.2 levels and up to 88 levels at
+    chroma edges (it replicates chroma; TurboJPEG's default is the triangle filter) -- the reason the upsampling
+    and the conversion are done by this repo's kernel."""
+    import os
+
+    R = rcv
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mjpeg_golden.npz"))
+    stats, lib_stats = {}, {}
+    names = ("444_q95", "420_q90", "422_q85", "420_odd_q92", "422_odd_q92", "gray_q90")
+    for name in names:
+        jpeg, want = g[f"jpeg_{name}"], g[f"bgr_{name}"]
+        h, w = want.shape[:2]
+        assert R.videoio.mjpeg_info(jpeg) == (w, h)
+        host = R.Mat.empty()
+        assert R.videoio.decode_frame(jpeg, 0, 0, R.videoio.MJPEG, host)
+        assert (host.rows, host.cols, host.channels, host.step) == (h, w, 3, w * 3)
+        dev = R.Mat.device_new(h, w, 3)
+        assert R.videoio.decode_frame(jpeg, w, h, R.videoio.MJPEG, dev)
+        got = host.to_numpy()
+        assert (dev.to_numpy() == got).all(), "host and device destinations hold the same decode"
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        stats[name] = (int(d.max()), round(float(d.mean()), 3))
+        R.imgproc.set_option("mjpeg.library_color", 1)
+        try:
+            lib = R.Mat.empty()
+            R.videoio.decode_frame(jpeg, 0, 0, R.videoio.MJPEG, lib)
+        finally:
+            R.imgproc.set_option("mjpeg.library_color", 0)
+        dl = np.abs(lib.to_numpy().astype(np.int32) - want.astype(np.int32))
+        lib_stats[name] = (int(dl.max()), round(float(dl.mean()), 3))
+    print("mjpeg vs libjpeg-turbo (max, mean):", stats)
+    print("nvJPEG's own colour path   (max, mean):", lib_stats)
+    for name, (mx, mean) in stats.items():
+        assert mx <= 4, (name, mx)
+        assert mean <= 0.1, (name, mean)
+    for name, (mx, mean) in lib_stats.items():
+        assert mean <= 4.0, (name, mean)
+    # contract: garbage and wrongly sized destinations are errors
+    from rustcv_b200 import _ffi as F
+    junk = np.arange(64, dtype=np.uint8)
+    m = R.Mat.new(8, 8, 3)
+    assert F.lib.rcv_mjpeg_to_bgr(junk.ctypes.data, junk.size, C.byref(m.c())) == F.RCV_ERR_ARG
+    jpeg = g["jpeg_444_q95"]
+    assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(m.c())) == F.RCV_ERR_SIZE
+    g1 = R.Mat.new(64, 96, 1)
+    assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(g1.c())) == F.RCV_ERR_DEPTH
