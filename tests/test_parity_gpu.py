@@ -1324,3 +1324,63 @@ def test_mjpeg_decode_matches_libjpeg_turbo_within_tolerance(rcv):
     assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(m.c())) == F.RCV_ERR_SIZE
     g1 = R.Mat.new(64, 96, 1)
     assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(g1.c())) == F.RCV_ERR_DEPTH
+
+
+def test_fused_chains_random_geometries(rcv, oracle):
+    """40 random (rows, even cols, band height, location) draws for both fused decode -> process kernels: every
+    right-edge phase, band seam and partial chunk they can meet, against the oracle's stand-alone stages."""
+    R = rcv
+    rng = np.random.default_rng(20261018)
+    for it in range(40):
+        h = int(rng.integers(8, 200))
+        w = 2 * int(rng.integers(4, 420))
+        band = int(rng.choice([0, 4, 12, 20, 36, 60]))
+        where = str(rng.choice(["device", "host", "pinned"]))
+        y = rng.integers(0, 256, size=(h, w, 2), dtype=np.uint8)
+        R.imgproc.set_option("yuyvgauss.band_rows", band)
+        R.imgproc.set_option("yuyvsobel.band_rows", band)
+        try:
+            s = mats(R, y, where)
+            d = out_like(R, s, where, channels=3)
+            R.imgproc.yuyv_to_bgr_gaussian5(s, d)
+            assert_same(d.to_numpy(), _yuyv_gauss_oracle(oracle, y), f"rand yuyv-gauss it{it} {h}x{w} band{band} {where}")
+            m = out_like(R, s, where, channels=1, depth=R.F32)
+            R.imgproc.yuyv_to_sobel_mag(s, m)
+            assert_f32(m.to_numpy(), _yuyv_sobel_oracle(oracle, y), f"rand yuyv-sobel it{it} {h}x{w} band{band} {where}", max_ulp=0)
+        finally:
+            R.imgproc.set_option("yuyvgauss.band_rows", 0)
+            R.imgproc.set_option("yuyvsobel.band_rows", 0)
+
+
+def test_fused_chains_full_size_equal_the_unfused_kernels(rcv, oracle):
+    """At camera sizes (4K and 1080p YUYV frames) the oracle chain takes a while, so the size-independent property
+    is used: the fused kernel and the library's stand-alone kernels run back to back give identical bytes; one
+    1080p frame is also checked against the oracle."""
+    R = rcv
+    for h, w in ((2160, 3840), (1080, 1920)):
+        y = oracle.fill_u8(900 + h, h * w * 2).reshape(h, w, 2)
+        s = R.Mat.from_numpy(y).upload()
+        a, b = s.like(channels=3), s.like(channels=3)
+        R.imgproc.yuyv_to_bgr_gaussian5(s, a)
+        R.imgproc.set_option("yuyvgauss.force_chain", 1)
+        try:
+            R.imgproc.yuyv_to_bgr_gaussian5(s, b)
+        finally:
+            R.imgproc.set_option("yuyvgauss.force_chain", 0)
+        an = a.to_numpy()
+        assert_same(an, b.to_numpy(), f"fused vs unfused gauss chain {h}x{w}")
+        ma, mb = s.like(channels=1, depth=R.F32), s.like(channels=1, depth=R.F32)
+        R.imgproc.yuyv_to_sobel_mag(s, ma)
+        R.imgproc.set_option("yuyvsobel.force_chain", 1)
+        try:
+            R.imgproc.yuyv_to_sobel_mag(s, mb)
+        finally:
+            R.imgproc.set_option("yuyvsobel.force_chain", 0)
+        assert_f32(ma.to_numpy(), mb.to_numpy(), f"fused vs unfused sobel chain {h}x{w}", max_ulp=0)
+        if h == 1080:
+            oracle.set_threads(8)
+            try:
+                assert_same(an, _yuyv_gauss_oracle(oracle, y), "1080p fused gauss chain vs oracle")
+                assert_f32(ma.to_numpy(), _yuyv_sobel_oracle(oracle, y), "1080p fused sobel chain vs oracle", max_ulp=0)
+            finally:
+                oracle.set_threads(1)
