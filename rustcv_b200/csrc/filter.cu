@@ -236,6 +236,7 @@ void gaussian_kernel_q8(int n, double sigma, int32_t *kq) {
 }
 
 int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_gauss3_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
 int launch_gaussq8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, const int32_t *ky, int ks,
                          cudaStream_t s);
 
@@ -255,6 +256,11 @@ int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh
                            ky[1] == 64 && ky[2] == 96;
     if (binomial5 && opt_get("gauss.force_generic", 0) == 0) {
       int rc = launch_gauss5_strip(c, src, dst, s);
+      if (rc != RCV_ERR_UNSUPPORTED) return rc;
+    }
+    const bool binomial3 = kw == 3 && kh == 3 && kx[0] == 64 && kx[1] == 128 && ky[0] == 64 && ky[1] == 128;
+    if (binomial3 && opt_get("gauss.force_generic", 0) == 0 && opt_get("gauss.no_binomial3", 0) == 0) {
+      int rc = launch_gauss3_strip(c, src, dst, s);
       if (rc != RCV_ERR_UNSUPPORTED) return rc;
     }
     if (kw == kh && (kw == 3 || kw == 5 || kw == 7) && opt_get("gauss.force_generic", 0) == 0) {

@@ -26,7 +26,7 @@ for i in range(NF):
     F.check(F.lib.rcv_mat_upload(C.byref(host.c()), C.byref(src[i].c())))
 stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(0))
 R.imgproc.set_blocking(False)
-ALL = ["gauss.band_rows", "strip.dynamic", "strip.grid", "gauss.variant"]
+ALL = ["gauss.band_rows", "strip.dynamic", "strip.grid", "gauss.variant", "gauss.no_binomial3"]
 
 
 def run(cfg: str, steps=20):

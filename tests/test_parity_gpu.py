@@ -229,6 +229,39 @@ def test_gaussian5_binomial_strip_kernel(rcv, oracle, where, shape):
     assert_same(d.to_numpy(), oracle.gaussian_blur(a, (5, 5)), f"gauss5 {shape} {where}")
 
 
+@pytest.mark.parametrize("where", WHERE)
+@pytest.mark.parametrize("shape", GAUSS_SHAPES)
+def test_gaussian3_binomial_strip_kernel(rcv, oracle, where, shape):
+    """GaussianBlur ksize 3, sigma 0 (k_strip<Gauss3Op>): every edge combination vs the oracle, and bit-identical
+    to the any-sigma op it replaces for these taps."""
+    R = rcv
+    h, w, cn = shape
+    a = oracle.fill_u8(33 + h + w, h * w * cn).reshape(h, w, cn)
+    if cn == 1:
+        a = a.reshape(h, w)
+    s = mats(R, a, where)
+    d = out_like(R, s, where)
+    R.imgproc.gaussian_blur(s, d, (3, 3), 0.0)
+    want = oracle.gaussian_blur(a, (3, 3))
+    assert_same(d.to_numpy(), want, f"gauss3 {shape} {where}")
+    if where == "device":
+        for band in (8, 12, 100):
+            R.imgproc.set_option("gauss.band_rows", band)
+            try:
+                d2 = s.like()
+                R.imgproc.gaussian_blur(s, d2, (3, 3), 0.0)
+                assert_same(d2.to_numpy(), want, f"gauss3 {shape} band {band}")
+            finally:
+                R.imgproc.set_option("gauss.band_rows", 0)
+        R.imgproc.set_option("gauss.no_binomial3", 1)
+        try:
+            d3 = s.like()
+            R.imgproc.gaussian_blur(s, d3, (3, 3), 0.0)
+            assert_same(d3.to_numpy(), want, f"any-sigma op on binomial taps {shape}")
+        finally:
+            R.imgproc.set_option("gauss.no_binomial3", 0)
+
+
 @pytest.mark.parametrize("band_rows", [8, 12, 28, 36, 100])
 def test_gaussian5_band_seams(rcv, oracle, band_rows):
     """Band boundaries (warm-up rows) and multi-chunk pipelines must be seamless."""
