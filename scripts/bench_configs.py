@@ -211,6 +211,41 @@ def chain_gauss(n=32):
     src.free(); dst.free()
 
 
+def cvtbatch(n=32):
+    """Pointwise conversions on a batch of 4K frames (one launch): the formats of SURVEY.md 8f ranks 3-4."""
+    h, w = 2160, 3840
+    I = R.imgproc
+    bgr = R.Mat.device_batch(n, h, w, 3)
+    base = O.fill_u8(12, h * w * 3)
+    fill_batch(bgr, lambda i: np.roll(base, i * 31).reshape(h, w, 3))
+    for name, code, dcn, bpp in (("BGR->Gray", I.COLOR_BGR2GRAY, 1, 4), ("RGB<->BGR", I.COLOR_RGB2BGR, 3, 6),
+                                 ("BGR->XRGB32", I.COLOR_BGR2XRGB32, 4, 7)):
+        dst = R.Mat.device_batch(n, h, w, dcn)
+        ms = timeit(lambda: I.cvt_color_batch(bgr, dst, code))
+        report(f"cvt {name} 3840x2160 x{n}", ms, n * h * w, bpp, {})
+        dst.free()
+    bgra = R.Mat.device_batch(n, h, w, 4)
+    I.cvt_color_batch(bgr, bgra, I.COLOR_BGR2XRGB32)
+    out3 = R.Mat.device_batch(n, h, w, 3)
+    ms = timeit(lambda: I.cvt_color_batch(bgra, out3, I.COLOR_BGRA2BGR))
+    report(f"cvt BGRA->BGR 3840x2160 x{n}", ms, n * h * w, 7, {})
+    bgra.free()
+    yuyv = R.Mat.device_batch(n, h, w, 2)
+    yb = O.fill_u8(13, h * w * 2)
+    fill_batch(yuyv, lambda i: np.roll(yb, i * 31).reshape(h, w, 2))
+    for name, code in (("YUYV->BGR", I.COLOR_YUYV2BGR), ("UYVY->BGR", I.COLOR_UYVY2BGR)):
+        ms = timeit(lambda: I.cvt_color_batch(yuyv, out3, code))
+        report(f"cvt {name} 3840x2160 x{n}", ms, n * h * w, 5, {})
+    g = R.Mat.device_batch(n, h, w, 1)
+    ms = timeit(lambda: I.cvt_color_batch(yuyv, g, I.COLOR_YUYV2GRAY))
+    report(f"cvt YUYV->Gray 3840x2160 x{n}", ms, n * h * w, 3, {})
+    f = R.Mat.device_batch(n, h, w, 1, R.F32)
+    ms = timeit(lambda: [I.convert_to(g[i], f[i], R.F32, 1.0 / 255) for i in range(4)])
+    report("convertTo u8->f32 3840x2160 (4 launches of 1 frame)", ms, 4 * h * w, 5, {})
+    for b in (bgr, out3, yuyv, g, f):
+        b.free()
+
+
 def cfg5sweep(n=8):
     """warpAffine tile height sweep (warp.tile_rows = 32 / 48 / 64 / automatic), parity of frame 0 each time."""
     s = 4096
@@ -243,7 +278,7 @@ def cfg5sweep(n=8):
     src.free(); dst.free(); src8.free(); dst8.free()
 
 
-ALL = {"chain": chain, "chain_gauss": chain_gauss, "cfg5sweep": cfg5sweep, "cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
+ALL = {"cvtbatch": cvtbatch, "chain": chain, "chain_gauss": chain_gauss, "cfg5sweep": cfg5sweep, "cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5,
        "cfg4full": lambda: cfg4(256), "cfg5full": lambda: cfg5(64)}
 for name in (sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]):
     ALL[name]()
