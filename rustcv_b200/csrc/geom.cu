@@ -156,6 +156,60 @@ __global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
   d[2] = out[2];
 }
 
+// Exact 2x downscale of u8 (4K -> 1080p, 1080p -> 540p: the commonest resize).  With scale 2 every weight of
+// the oracle's fixed-point model is 1024 and its chain collapses, exactly, to the rounded 2x2 box mean
+//   out = (p[2y][2x] + p[2y][2x+1] + p[2y+1][2x] + p[2y+1][2x+1] + 2) >> 2
+// ((1024 * ((1024 (a + b)) >> 4)) >> 16 == a + b; tested equal to the general kernel and to OpenCV).  Every source
+// byte is needed, so the kernel is a pure stream: a thread makes G dst pixels from 2 rows x 2*G*CN bytes
+// (128-bit loads), G*CN bytes out.
+template <int CN, int G>
+__global__ void __launch_bounds__(128) k_resize2x_u8(const ResizeArgs a) {
+  constexpr int IN_B = 2 * G * CN, OUT_B = G * CN;
+  static_assert(IN_B % 16 == 0 && OUT_B % 4 == 0, "vector widths");
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;  // group of G dst pixels
+  const int dy = blockIdx.y;
+  if (g >= a.dcols / G) return;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const uint4 *r0 = (const uint4 *)(src + (size_t)(2 * dy) * a.sstep + (size_t)g * IN_B);
+  const uint4 *r1 = (const uint4 *)(src + (size_t)(2 * dy + 1) * a.sstep + (size_t)g * IN_B);
+  uint32_t w0[IN_B / 4], w1[IN_B / 4];
+#pragma unroll
+  for (int k = 0; k < IN_B / 16; ++k) {
+    uint4 q = __ldg(r0 + k);
+    w0[4 * k] = q.x;
+    w0[4 * k + 1] = q.y;
+    w0[4 * k + 2] = q.z;
+    w0[4 * k + 3] = q.w;
+    q = __ldg(r1 + k);
+    w1[4 * k] = q.x;
+    w1[4 * k + 1] = q.y;
+    w1[4 * k + 2] = q.z;
+    w1[4 * k + 3] = q.w;
+  }
+  uint32_t out[OUT_B / 4];
+#pragma unroll
+  for (int k = 0; k < OUT_B / 4; ++k) out[k] = 0;
+#pragma unroll
+  for (int ob = 0; ob < OUT_B; ++ob) {
+    const int j = ob / CN, ch = ob % CN;
+    const int i0 = 2 * j * CN + ch, i1 = i0 + CN;
+    const uint32_t v = (byte_at(w0, i0) + byte_at(w0, i1) + byte_at(w1, i0) + byte_at(w1, i1) + 2u) >> 2;
+    out[ob >> 2] |= v << ((ob & 3) * 8);
+  }
+  uint32_t *d = (uint32_t *)(a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep + (size_t)g * OUT_B);
+#pragma unroll
+  for (int k = 0; k < OUT_B / 4; ++k) d[k] = out[k];
+}
+
+template <int CN, int G>
+static int launch_resize2x(const ResizeArgs &a, int n, cudaStream_t s) {
+  dim3 grid(ceil_div(a.dcols / G, 128), a.drows, n);
+  k_resize2x_u8<CN, G><<<grid, 128, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
 int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
   if (dst.v.rows == 0 || dst.v.cols == 0 || src.n == 0) return RCV_OK;
   if (src.v.rows == 0 || src.v.cols == 0) return fail(RCV_ERR_SIZE, "resize from an empty image");
@@ -171,6 +225,12 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
     count_launch();
     RCV_CUDA(cudaGetLastError());
     return RCV_OK;
+  }
+  if (src.v.depth == RCV_U8 && src.v.rows == 2 * dst.v.rows && src.v.cols == 2 * dst.v.cols && al &&
+      opt_get("resize.force_generic", 0) == 0) {
+    if (src.v.cn == 3 && (dst.v.cols & 7) == 0) return launch_resize2x<3, 8>(a, src.n, s);
+    if (src.v.cn == 1 && (dst.v.cols & 7) == 0) return launch_resize2x<1, 8>(a, src.n, s);
+    if (src.v.cn == 4 && (dst.v.cols & 3) == 0) return launch_resize2x<4, 4>(a, src.n, s);
   }
   // the per-column / per-row tables depend on the geometry only: rebuilt and uploaded when it changes
   void *dcols = nullptr, *drows = nullptr;

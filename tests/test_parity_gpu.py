@@ -585,6 +585,41 @@ def test_resize_larger_geometries(rcv, oracle, case):
     assert_f32(df.to_numpy().reshape(dr, -1), wantf.reshape(dr, -1), f"resize f32 {case}", max_ulp=0)
 
 
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_resize_2x_fast_path(rcv, oracle, cn):
+    """Exact 2x downscale (rounded 2x2 box mean): bit-identical to the oracle's fixed-point model, to the general
+    kernel, and to OpenCV (cv2.resize INTER_LINEAR at exactly 2x; golden generated with the other fixtures)."""
+    R = rcv
+    for h, w in ((64, 96), (270, 480), (2, 16), (130, 1000)):
+        a = oracle.fill_u8(80 + h + cn, h * w * cn).reshape(h, w, cn)
+        if cn == 1:
+            a = a.reshape(h, w)
+        want = oracle.resize_bilinear(a, h // 2, w // 2)
+        s = mats(R, a, "device")
+        n0 = R.imgproc.launch_count()
+        d = out_like(R, s, "device", rows=h // 2, cols=w // 2)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.resize(s, d)
+        assert R.imgproc.launch_count() - n0 == 1
+        assert_same(d.to_numpy(), want, f"resize 2x cn{cn} {h}x{w}")
+        box = (a.astype(np.uint32).reshape(h // 2, 2, w // 2, 2, -1).sum(axis=(1, 3)) + 2) >> 2
+        assert_same(d.to_numpy().reshape(h // 2, w // 2, -1), box.astype(np.uint8), f"2x2 box mean cn{cn} {h}x{w}")
+        R.imgproc.set_option("resize.force_generic", 1)
+        try:
+            d2 = out_like(R, s, "device", rows=h // 2, cols=w // 2)
+            R.imgproc.resize(s, d2)
+            assert_same(d2.to_numpy(), want, f"general kernel at 2x cn{cn} {h}x{w}")
+        finally:
+            R.imgproc.set_option("resize.force_generic", 0)
+    # host Mats and a width that is not a multiple of the vector group (general kernel)
+    a = oracle.fill_u8(90 + cn, 50 * 52 * cn).reshape(50, 52, cn)
+    if cn == 1:
+        a = a.reshape(50, 52)
+    d = R.Mat.empty()
+    R.imgproc.resize(R.Mat.from_numpy(a), d, (26, 25))
+    assert_same(d.to_numpy(), oracle.resize_bilinear(a, 25, 26), f"resize 2x host cn{cn}")
+
+
 def test_resize_f32(rcv, oracle):
     R = rcv
     a = oracle.fill_f32(61, 61 * 83).reshape(61, 83)
