@@ -100,3 +100,52 @@ pub fn yuyv_to_bgr(src: &[u8], dest: &mut [u8], width: usize, height: usize) -> 
 pub fn bgra_to_bgr(src: &[u8], dest: &mut [u8], width: usize, height: usize) -> Result<()> {
     check(unsafe { sys::rcv_bgra_to_bgr_packed(src.as_ptr(), src.len(), dest.as_mut_ptr(), dest.len(), width, height) })
 }
+
+/// Replaces the TurboJPEG branch of `VideoCapture::read` (rustcv/src/videoio/mod.rs:205-232; `decode_mjpeg`,
+/// rustcv-camera/src/decode.rs:93-121): header first, then decompress to BGR at the Mat's pitch.
+pub fn mjpeg_to_bgr(data: &[u8], mat: &mut Mat) -> Result<()> {
+    let (mut w, mut h) = (0i32, 0i32);
+    check(unsafe { sys::rcv_mjpeg_info(data.as_ptr(), data.len(), &mut w, &mut h) })?;
+    ensure_size(mat, h, w, 3);
+    let mut d = pod(mat);
+    check(unsafe { sys::rcv_mjpeg_to_bgr(data.as_ptr(), data.len(), &mut d) })
+}
+
+/// The raw YUYV frame of `read()` (videoio/mod.rs:201-203) as a 2-channel Mat view: no copy.
+fn yuyv_pod(data: &[u8], width: i32, height: i32, stride: usize) -> sys::RcvMat {
+    sys::RcvMat {
+        data: data.as_ptr() as *mut _,
+        rows: height,
+        cols: width,
+        step: if stride != 0 { stride } else { width as usize * 2 },
+        channels: 2,
+        depth: sys::RCV_U8,
+        loc: sys::RCV_HOST,
+        reserved: 0,
+        device: 0,
+    }
+}
+
+/// Fused decode -> process: GaussianBlur5x5(YUYV2BGR(frame)) in one kernel, the BGR intermediate never exists.
+pub fn yuyv_to_bgr_gaussian5(data: &[u8], width: i32, height: i32, stride: usize, dst: &mut Mat) -> Result<()> {
+    ensure_size(dst, height, width, 3);
+    let (s, mut d) = (yuyv_pod(data, width, height, stride), pod(dst));
+    check(unsafe { sys::rcv_yuyv_to_bgr_gaussian5(&s, &mut d) })
+}
+
+/// Fused decode -> process: Sobel magnitude (f32) of the frame's gray image in one kernel.  `mag` holds
+/// rows x cols f32 values in `data` (step in bytes), the f32 Mat convention of include/rcv_imgproc.h.
+pub fn yuyv_to_sobel_magnitude(data: &[u8], width: i32, height: i32, stride: usize, mag: &mut Mat) -> Result<()> {
+    let step = width as usize * 4;
+    if mag.data.len() != height as usize * step {
+        mag.data = vec![0; height as usize * step];
+    }
+    mag.rows = height;
+    mag.cols = width;
+    mag.channels = 1;
+    mag.step = step;
+    let s = yuyv_pod(data, width, height, stride);
+    let mut d = pod(mag);
+    d.depth = sys::RCV_F32;
+    check(unsafe { sys::rcv_yuyv_to_sobel_mag(&s, &mut d) })
+}
