@@ -210,6 +210,80 @@ static int launch_resize2x(const ResizeArgs &a, int n, cudaStream_t s) {
   return RCV_OK;
 }
 
+// Exact 2x upscale of u8 (1080p -> 4K).  With scale 1/2 the oracle's weights are 512 / 1536 (and 2048 / 0 at
+// the clamped edge columns), and its fixed-point chain collapses, exactly, to
+//   H(row, dst col)  = c[far] + 3 c[near]          far = the source pixel on the other side, clamped to the row
+//   out(dst row, .)  = ((H[far row] >> 2) + ((3 H[near row]) >> 2) + 2) >> 2      rows clamped likewise
+// (checked against the oracle and OpenCV for all channel counts, tests + the derivation in DESIGN.md).  A thread
+// takes G source pixels of one source row and writes the 2 x 2G destination pixels they own: 3 rows x (G+2)
+// pixels in (word loads), 2 x 2*G*CN bytes out (64-bit stores) -- the kernel is bound by its 4x larger output.
+template <int CN, int G>
+__global__ void __launch_bounds__(128) k_resize_up2x_u8(const ResizeArgs a) {
+  constexpr int IN_B = G * CN, NW = IN_B / 4 + 2;  // main words + one halo word on each side
+  static_assert(IN_B % 4 == 0, "whole words");
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;  // group of G source pixels
+  const int j = blockIdx.y;                             // source row
+  const int groups = a.scols / G;
+  if (g >= groups) return;
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const int jr[3] = {max(j - 1, 0), j, min(j + 1, a.srows - 1)};
+  int cv[3][G + 2][CN];  // [row][pixel -1 .. G][channel]
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const uint32_t *row = (const uint32_t *)(src + (size_t)jr[r] * a.sstep + (size_t)g * IN_B);
+    uint32_t w[NW];
+    w[0] = g > 0 ? __ldg(row - 1) : 0u;
+#pragma unroll
+    for (int k = 0; k < IN_B / 4; ++k) w[k + 1] = __ldg(row + k);
+    w[NW - 1] = g + 1 < groups ? __ldg(row + IN_B / 4) : 0u;
+#pragma unroll
+    for (int p = -1; p <= G; ++p)
+#pragma unroll
+      for (int ch = 0; ch < CN; ++ch) cv[r][p + 1][ch] = (int)byte_at(w, 4 + p * CN + ch);
+#pragma unroll
+    for (int ch = 0; ch < CN; ++ch) {  // clamp the halo pixels at the ends of the row
+      if (g == 0) cv[r][0][ch] = cv[r][1][ch];
+      if (g + 1 == groups) cv[r][G + 1][ch] = cv[r][G][ch];
+    }
+  }
+  uint32_t out[2][2 * IN_B / 4];
+#pragma unroll
+  for (int k = 0; k < 2 * IN_B / 4; ++k) out[0][k] = out[1][k] = 0;
+#pragma unroll
+  for (int p = 0; p < G; ++p)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)  // destination column 2p + e: far = p-1 (even) or p+1 (odd)
+#pragma unroll
+      for (int ch = 0; ch < CN; ++ch) {
+        const int fp = e ? p + 2 : p;  // index of the far pixel in cv (pixel + 1)
+        const int hu = cv[0][fp][ch] + 3 * cv[0][p + 1][ch];
+        const int hm = cv[1][fp][ch] + 3 * cv[1][p + 1][ch];
+        const int hd = cv[2][fp][ch] + 3 * cv[2][p + 1][ch];
+        const int m3 = (3 * hm) >> 2;
+        const uint32_t v0 = (uint32_t)(((hu >> 2) + m3 + 2) >> 2);  // destination row 2j
+        const uint32_t v1 = (uint32_t)(((hd >> 2) + m3 + 2) >> 2);  // destination row 2j + 1
+        const int ob = (2 * p + e) * CN + ch;
+        out[0][ob >> 2] |= v0 << ((ob & 3) * 8);
+        out[1][ob >> 2] |= v1 << ((ob & 3) * 8);
+      }
+  uint8_t *d0 = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)(2 * j) * a.dstep + (size_t)g * 2 * IN_B;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    uint2 *d = (uint2 *)(d0 + (size_t)rr * a.dstep);
+#pragma unroll
+    for (int k = 0; k < IN_B / 4; ++k) d[k] = make_uint2(out[rr][2 * k], out[rr][2 * k + 1]);
+  }
+}
+
+template <int CN, int G>
+static int launch_resize_up2x(const ResizeArgs &a, int n, cudaStream_t s) {
+  dim3 grid(ceil_div(a.scols / G, 128), a.srows, n);
+  k_resize_up2x_u8<CN, G><<<grid, 128, 0, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
 int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) {
   if (dst.v.rows == 0 || dst.v.cols == 0 || src.n == 0) return RCV_OK;
   if (src.v.rows == 0 || src.v.cols == 0) return fail(RCV_ERR_SIZE, "resize from an empty image");
@@ -231,6 +305,13 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
     if (src.v.cn == 3 && (dst.v.cols & 7) == 0) return launch_resize2x<3, 8>(a, src.n, s);
     if (src.v.cn == 1 && (dst.v.cols & 7) == 0) return launch_resize2x<1, 8>(a, src.n, s);
     if (src.v.cn == 4 && (dst.v.cols & 3) == 0) return launch_resize2x<4, 4>(a, src.n, s);
+  }
+  if (src.v.depth == RCV_U8 && dst.v.rows == 2 * src.v.rows && dst.v.cols == 2 * src.v.cols && src.v.rows <= 65535 &&
+      ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 3) == 0) &&
+      ((((uintptr_t)dst.v.data | dst.v.step | dst.frame_stride) & 7) == 0) && opt_get("resize.force_generic", 0) == 0) {
+    if (src.v.cn == 3 && (src.v.cols & 3) == 0) return launch_resize_up2x<3, 4>(a, src.n, s);
+    if (src.v.cn == 1 && (src.v.cols & 3) == 0) return launch_resize_up2x<1, 4>(a, src.n, s);
+    if (src.v.cn == 4 && (src.v.cols & 1) == 0) return launch_resize_up2x<4, 2>(a, src.n, s);
   }
   // the per-column / per-row tables depend on the geometry only: rebuilt and uploaded when it changes
   void *dcols = nullptr, *drows = nullptr;

@@ -620,6 +620,54 @@ def test_resize_2x_fast_path(rcv, oracle, cn):
     assert_same(d.to_numpy(), oracle.resize_bilinear(a, 25, 26), f"resize 2x host cn{cn}")
 
 
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_resize_2x_upscale_fast_path(rcv, oracle, cn):
+    """Exact 2x upscale (k_resize_up2x_u8): the fixed-point model's closed form at scale 1/2 -- bit-identical to the
+    oracle (itself bit-identical to OpenCV there), to the general kernel, and to the closed form written in numpy;
+    edge rows / columns (clamped far taps), single-row and single-group images included."""
+    R = rcv
+    for h, w in ((32, 48), (135, 240), (1, 4), (7, 4), (1, 400), (61, 1000)):
+        a = oracle.fill_u8(85 + h + cn, h * w * cn).reshape(h, w, cn)
+        a3 = a.astype(np.int64)
+        if cn == 1:
+            a = a.reshape(h, w)
+        want = oracle.resize_bilinear(a, 2 * h, 2 * w)
+        dx, dy = np.arange(2 * w), np.arange(2 * h)
+        far = np.where(dx % 2 == 0, np.maximum(dx // 2 - 1, 0), np.minimum(dx // 2 + 1, w - 1))
+        farr = np.where(dy % 2 == 0, np.maximum(dy // 2 - 1, 0), np.minimum(dy // 2 + 1, h - 1))
+        H = a3[:, far, :] + 3 * a3[:, dx // 2, :]
+        closed = (((H[farr] >> 2) + ((3 * H[dy // 2]) >> 2) + 2) >> 2).astype(np.uint8)
+        assert_same(closed.reshape(want.shape), want, f"closed form vs oracle cn{cn} {h}x{w}")
+        s = mats(R, a, "device")
+        d = out_like(R, s, "device", rows=2 * h, cols=2 * w)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.resize(s, d)
+        assert R.imgproc.launch_count() - n0 == 1
+        assert_same(d.to_numpy(), want, f"resize up 2x cn{cn} {h}x{w}")
+        R.imgproc.set_option("resize.force_generic", 1)
+        try:
+            d2 = out_like(R, s, "device", rows=2 * h, cols=2 * w)
+            R.imgproc.resize(s, d2)
+            assert_same(d2.to_numpy(), want, f"general kernel at 1/2 cn{cn} {h}x{w}")
+        finally:
+            R.imgproc.set_option("resize.force_generic", 0)
+    a = oracle.fill_u8(95 + cn, 30 * 44 * cn).reshape(30, 44, cn)
+    if cn == 1:
+        a = a.reshape(30, 44)
+    d = R.Mat.empty()
+    R.imgproc.resize(R.Mat.from_numpy(a), d, (88, 60))
+    assert_same(d.to_numpy(), oracle.resize_bilinear(a, 60, 88), f"resize up 2x host cn{cn}")
+    # a batch (frames in blockIdx.z)
+    frames = [oracle.fill_u8(96 + k, 40 * 64 * cn).reshape((40, 64, cn) if cn > 1 else (40, 64)) for k in range(3)]
+    sb, db = R.Mat.device_batch(3, 40, 64, cn), R.Mat.device_batch(3, 80, 128, cn)
+    for k in range(3):
+        upload_into(R, frames[k], sb[k])
+    R.imgproc.resize_batch(sb, db)
+    for k in range(3):
+        assert_same(db[k].to_numpy(), oracle.resize_bilinear(frames[k], 80, 128), f"resize up 2x batch {k} cn{cn}")
+    sb.free(); db.free()
+
+
 def test_resize_f32(rcv, oracle):
     R = rcv
     a = oracle.fill_f32(61, 61 * 83).reshape(61, 83)
