@@ -1,9 +1,13 @@
-// stencil.cu -- TMA strip-pipeline stencil kernels for sm_100a:
-//   k_strip<Gauss5Op<CN>>   5x5 binomial GaussianBlur on u8 (the BASELINE.json metric kernel)
-//   k_strip<Sobel3Op>       Sobel 3x3 + gradient magnitude on f32
+// strip_pipeline.cuh -- the TMA strip pipeline shared by the stencil / fused-chain kernels for sm_100a:
+//   k_strip<Gauss5Op<CN>>      5x5 binomial GaussianBlur on u8 (the BASELINE.json metric kernel)   strip_gauss5.cu
+//   k_strip<Gauss3Op<CN>>      3x3 binomial GaussianBlur on u8                                      strip_gauss3.cu
+//   k_strip<GaussQ8Op<CN,KS>>  any-sigma 3x3 / 5x5 / 7x7 GaussianBlur on u8                          strip_gaussq8*.cu
+//   k_strip<Sobel3Op<ALL>>     Sobel 3x3 + gradient magnitude on f32                                strip_sobel.cu
+//   k_strip<SepF32Op / Filter2dF32Op / Filter2dU8Op>   separable and dense filters                  strip_f32.cu, strip_f2d_u8.cu
+//   k_strip<YuyvSobelOp>, k_strip<YuyvGauss5Op>        fused decode -> process chains               strip_yuyv_*.cu
 //
 // The reference has no such ops (rustcv/src/imgproc/mod.rs:1-4 is drawing only); the
-// semantics are the oracle's (oracle/rcv_oracle.c: orc_sepfilter_u8_q8, orc_sobel3_f32),
+// semantics are the oracle's (oracle/rcv_oracle.c: orc_sepfilter_u8_q8, orc_sobel3_f32, ...),
 // which are OpenCV's (README.md:19,30 "OpenCV parity").
 //
 // Design:
@@ -19,10 +23,12 @@
 //     source row is read from shared memory exactly once and the vertical pass needs no
 //     re-reads; the horizontal pass takes its neighbours by warp shuffle.
 //   * u8 arithmetic is SIMD-in-register: two samples per 32-bit register as 16-bit lanes
-//     (vertical sums <= 4080, final sums <= 65408 fit exactly), PRMT for the stride-CN
+//     (vertical sums <= 4088, final sums <= 65408 fit exactly), PRMT for the stride-CN
 //     byte gathers.
 //   * BORDER_REFLECT_101 is produced by patching the landed tile in shared memory
 //     (TMA out-of-bounds fill is zeros), only in edge strips/bands.
+//   * A launch may be restricted to a row window (the banded host pipeline of abi.cu), and a job smaller
+//     than the machine is cut so that its items fill one round (pick_band_rows).
 #pragma once
 
 #include "rcv_internal.cuh"
