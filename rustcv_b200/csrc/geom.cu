@@ -156,6 +156,74 @@ __global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
   d[2] = out[2];
 }
 
+// General resize of u8 C3 / C4, word loads.  k_resize_generic is bound by its load/store unit traffic (12 byte
+// loads and 3 byte stores per BGR pixel, each warp-wide load two wavefronts wide).  The two taps of a row are
+// adjacent pixels, i.e. 2*CN contiguous bytes: here they are fetched as the aligned 32-bit words that cover them
+// and moved into place with funnel shifts (6 word loads per BGR pixel instead of 12 byte loads), and a thread
+// makes 4 destination pixels so that its output leaves as words.  Same fixed-point arithmetic.
+template <int CN>
+__global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
+  static_assert(CN == 3 || CN == 4, "BGR / BGRA");
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 destination pixels
+  const int dy = blockIdx.y;
+  const int dx0 = 4 * t;
+  if (dx0 >= a.dcols) return;
+  const ResizeRow r = a.rows[dy];
+  const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
+  const uint32_t *s0 = (const uint32_t *)(src + (size_t)r.y0 * a.sstep);
+  const uint32_t *s1 = (const uint32_t *)(src + (size_t)r.y1 * a.sstep);
+  const int last_word = (a.scols * CN - 1) >> 2;  // the last word holding row bytes
+  uint32_t ob[4 * CN];                            // output bytes of the 4 pixels
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int dx = min(dx0 + q, a.dcols - 1);  // a ragged last group recomputes its last pixel (not stored)
+    const int2 xx = *(const int2 *)&a.cols[dx].x0;
+    const int2 aa = *(const int2 *)&a.cols[dx].a0;
+    const int o = xx.x * CN, wi = o >> 2, sh = (o & 3) * 8;
+    uint32_t p0[2][CN], p1[2][CN];  // [row][channel]: tap (x0) and tap (x1)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const uint32_t *row = rr ? s1 : s0;
+      const uint32_t w0 = __ldg(row + wi), w1 = __ldg(row + min(wi + 1, last_word));
+      uint32_t lo, hi;
+      if (CN == 4) {
+        lo = w0;  // o is a multiple of 4: the two pixels are the two words
+        hi = w1;
+      } else {
+        const uint32_t w2 = __ldg(row + min(wi + 2, last_word));
+        lo = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
+        hi = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
+      }
+#pragma unroll
+      for (int ch = 0; ch < CN; ++ch) {
+        p0[rr][ch] = (lo >> (8 * ch)) & 0xFFu;
+        const int k = CN + ch;  // byte index of the second tap
+        p1[rr][ch] = ((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4)))) & 0xFFu;
+        if (xx.y == xx.x) p1[rr][ch] = p0[rr][ch];  // clamped at the right edge: x1 == x0
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CN; ++ch) {
+      const int S0 = (int)p0[0][ch] * aa.x + (int)p1[0][ch] * aa.y;
+      const int S1 = (int)p0[1][ch] * aa.x + (int)p1[1][ch] * aa.y;
+      const int v = (((r.b0 * (S0 >> 4)) >> 16) + ((r.b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+      ob[q * CN + ch] = (uint32_t)min(max(v, 0), 255);
+    }
+  }
+  uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep + (size_t)dx0 * CN;
+  if (dx0 + 4 <= a.dcols) {
+    uint32_t *dw = (uint32_t *)d;  // 4*CN bytes, 4-byte aligned (dst base and step are)
+#pragma unroll
+    for (int k = 0; k < CN; ++k)
+      dw[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | (ob[4 * k + 3] << 24);
+  } else {
+    const int n = (a.dcols - dx0) * CN;
+#pragma unroll
+    for (int k = 0; k < 4 * CN; ++k)
+      if (k < n) d[k] = (uint8_t)ob[k];
+  }
+}
+
 // Exact 2x downscale of u8 (4K -> 1080p, 1080p -> 540p: the commonest resize).  With scale 2 every weight of
 // the oracle's fixed-point model is 1024 and its chain collapses, exactly, to the rounded 2x2 box mean
 //   out = (p[2y][2x] + p[2y][2x+1] + p[2y+1][2x] + p[2y+1][2x+1] + 2) >> 2
@@ -330,6 +398,21 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
   }
   a.cols = (const ResizeCol *)dcols;
   a.rows = (const ResizeRow *)drows;
+  // u8 BGR / BGRA with word-aligned rows on both sides: the word-load kernel (rows must be readable up to the
+  // word that holds their last byte: step >= row bytes rounded up to 4)
+  if (src.v.depth == RCV_U8 && (src.v.cn == 3 || src.v.cn == 4) && opt_get("resize.force_generic", 0) == 0 &&
+      opt_get("resize.byte_loads", 0) == 0 && ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 3) == 0) &&
+      ((((uintptr_t)dst.v.data | dst.v.step | dst.frame_stride) & 3) == 0) &&
+      src.v.step >= (((size_t)src.v.cols * src.v.cn + 3) & ~(size_t)3)) {
+    dim3 gridw(ceil_div(ceil_div(dst.v.cols, 4), 128), dst.v.rows, src.n);
+    if (src.v.cn == 3)
+      k_resize_u8w<3><<<gridw, 128, 0, s>>>(a);
+    else
+      k_resize_u8w<4><<<gridw, 128, 0, s>>>(a);
+    count_launch();
+    RCV_CUDA(cudaGetLastError());
+    return RCV_OK;
+  }
   dim3 grid(ceil_div(dst.v.cols, 256), dst.v.rows, src.n);
   if (src.v.depth == RCV_U8)
     k_resize_generic<uint8_t><<<grid, 256, 0, s>>>(a);
