@@ -232,3 +232,102 @@ def test_convert_to_model(oracle):
     cv2 = pytest.importorskip("cv2")
     assert np.abs(cv2.convertScaleAbs(v) .astype(int) - oracle.convert_to(np.abs(v), np.uint8).astype(int)).max() <= 1
     assert (oracle.convert_to(u, np.float32) == u.astype(np.float32)).all()
+
+
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_resize_closed_forms_at_exact_scales(oracle, cn):
+    """The closed forms the fast-path kernels implement (k_resize2x_u8, k_resize_up2x_u8, k_resize4x_u8c3) ARE
+    the oracle's fixed-point model at scales 2, 1/2 and 4 -- and OpenCV's, where cv2 is installed."""
+    rng = np.random.default_rng(40 + cn)
+    h, w = 24, 36
+    a = rng.integers(0, 256, size=(h, w, cn), dtype=np.uint8)
+    a3 = a.astype(np.int64)
+    img = a.reshape(h, w) if cn == 1 else a
+    # 2x down: rounded 2x2 box mean
+    box2 = ((a3.reshape(h // 2, 2, w // 2, 2, cn).sum(axis=(1, 3)) + 2) >> 2).astype(np.uint8)
+    down2 = oracle.resize_bilinear(img, h // 2, w // 2).reshape(h // 2, w // 2, cn)
+    assert (down2 == box2).all()
+    # 4x down: the middle 2x2 of every 4x4
+    mid = a3.reshape(h // 4, 4, w // 4, 4, cn)[:, 1:3, :, 1:3, :]
+    box4 = ((mid.sum(axis=(1, 3)) + 2) >> 2).astype(np.uint8)
+    assert (oracle.resize_bilinear(img, h // 4, w // 4).reshape(h // 4, w // 4, cn) == box4).all()
+    # 2x up: H = c[far] + 3 c[near]; out = ((H_far >> 2) + ((3 H_near) >> 2) + 2) >> 2, far taps clamped
+    dx, dy = np.arange(2 * w), np.arange(2 * h)
+    far = np.where(dx % 2 == 0, np.maximum(dx // 2 - 1, 0), np.minimum(dx // 2 + 1, w - 1))
+    farr = np.where(dy % 2 == 0, np.maximum(dy // 2 - 1, 0), np.minimum(dy // 2 + 1, h - 1))
+    H = a3[:, far, :] + 3 * a3[:, dx // 2, :]
+    up2 = (((H[farr] >> 2) + ((3 * H[dy // 2]) >> 2) + 2) >> 2).astype(np.uint8)
+    assert (oracle.resize_bilinear(img, 2 * h, 2 * w).reshape(2 * h, 2 * w, cn) == up2).all()
+    cv2 = pytest.importorskip("cv2")
+    assert (cv2.resize(img, (w // 2, h // 2), interpolation=cv2.INTER_LINEAR).reshape(box2.shape) == box2).all()
+    assert (cv2.resize(img, (2 * w, 2 * h), interpolation=cv2.INTER_LINEAR).reshape(up2.shape) == up2).all()
+
+
+def test_gaussian3_binomial_closed_form(oracle):
+    """Gauss3Op's arithmetic: with Q8 taps {64,128,64} the oracle's (sum + 2^15) >> 16 is (S + 8) >> 4 of the
+    {1,2,1} x {1,2,1} sum S, which the kernel forms as the high byte of 16 S + 128."""
+    assert oracle.gaussian_kernel_q8(3, 0.0).tolist() == [64, 128, 64]
+    rng = np.random.default_rng(44)
+    img = rng.integers(0, 256, size=(19, 23), dtype=np.uint8)
+    p = np.pad(img.astype(np.int64), 1, mode="reflect")  # numpy "reflect" == BORDER_REFLECT_101
+    b = np.array([1, 2, 1])
+    S = sum(b[i] * b[j] * p[i:i + 19, j:j + 23] for i in range(3) for j in range(3))
+    want = oracle.gaussian_blur(img, (3, 3))
+    assert (((S + 8) >> 4) == want).all()
+    assert ((((16 * S + 128) >> 8) & 0xFF) == want).all() and (16 * S + 128).max() <= 65408
+
+
+def test_fused_sobel_chain_is_integer_exact(oracle):
+    """YuyvSobelOp keeps the Sobel sums of the gray image in integer registers: on u8-valued f32 input every
+    intermediate of orc_sobel3_f32 is an integer below 2^24, so the f32 chain and the integer chain agree and only
+    the final sqrtf rounds."""
+    rng = np.random.default_rng(45)
+    g = rng.integers(0, 256, size=(31, 37)).astype(np.int64)
+    g[3:9, 4:20] = 255
+    g[10:14, 0:9] = 0
+    out = oracle.sobel3(g.astype(np.float32), want=("gx", "gy", "mag"))
+    p = np.pad(g, 1, mode="reflect")
+    gx = (p[:-2, 2:] + 2 * p[1:-1, 2:] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[1:-1, :-2] + p[2:, :-2])
+    gy = (p[2:, :-2] + 2 * p[2:, 1:-1] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[:-2, 1:-1] + p[:-2, 2:])
+    assert (out["gx"] == gx).all() and (out["gy"] == gy).all()
+    ss = gx * gx + gy * gy
+    assert ss.max() < 2 ** 24
+    assert (out["mag"] == np.sqrt(ss.astype(np.float32))).all()  # numpy's f32 sqrt is correctly rounded too
+
+
+def test_mjpeg_fixture_is_what_libjpeg_turbo_decodes():
+    """tests/golden/mjpeg_golden.npz: the stored BGR frames are cv2.imdecode (libjpeg-turbo) of the stored JPEG
+    bytes -- the pin of the MJPEG branch (skipped where cv2 is absent, e.g. on the GPU box)."""
+    import os
+
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mjpeg_golden.npz"))
+    names = [k[5:] for k in g.files if k.startswith("jpeg_")]
+    assert len(names) >= 6
+    for n in names:
+        assert (cv2.imdecode(g[f"jpeg_{n}"], cv2.IMREAD_COLOR) == g[f"bgr_{n}"]).all(), n
+
+
+def test_mjpeg_colour_conversion_formula_is_libjpeg_turbos():
+    """k_ycc_to_bgr's fixed-point YCbCr -> BGR (csrc/mjpeg.cu: 91881 / 116130 / 22554 / 46802, ONE_HALF, arithmetic
+    shifts, clamp) applied to libjpeg's own full-resolution YCbCr output (Pillow, JCS_YCbCr) reproduces
+    libjpeg-turbo's BGR (cv2.imdecode) bit for bit on every fixture -- the CPU-side pin of that kernel's arithmetic;
+    its upsampling half is pinned on the GPU against the same BGR frames."""
+    import io
+    import os
+
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mjpeg_golden.npz"))
+    for n in ("444_q95", "420_q90", "422_q85", "420_odd_q92", "422_odd_q92"):
+        im = Image.open(io.BytesIO(g[f"jpeg_{n}"].tobytes()))
+        im.draft("YCbCr", im.size)
+        assert im.mode == "YCbCr"
+        ycc = np.asarray(im).astype(np.int64)
+        y, cb, cr = ycc[..., 0], ycc[..., 1] - 128, ycc[..., 2] - 128
+        r = y + ((91881 * cr + 32768) >> 16)
+        b = y + ((116130 * cb + 32768) >> 16)
+        gg = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16)
+        bgr = np.clip(np.stack([b, gg, r], -1), 0, 255).astype(np.uint8)
+        assert (bgr == g[f"bgr_{n}"]).all(), n
+        assert (bgr == cv2.imdecode(g[f"jpeg_{n}"], cv2.IMREAD_COLOR)).all(), n
