@@ -177,3 +177,27 @@ def test_fourcc_round_trip():
     from rustcv_b200 import videoio
 
     assert videoio.YUYV == 0x56595559 and videoio.MJPEG == 0x47504A4D
+
+
+def test_new_entry_points_validate_before_cuda_and_refuse_without_a_gpu():
+    """Fused chains and the MJPEG branch: argument contracts are checked before any CUDA call (so they are testable
+    here), and without an initialised B200 the calls refuse instead of falling back."""
+    import rustcv_b200 as R
+    from rustcv_b200 import _ffi as F
+
+    yuyv = R.Mat.new(8, 8, 2)
+    mag = R.Mat.new(8, 8, 1, R.F32)
+    assert F.lib.rcv_yuyv_to_sobel_mag(C.byref(R.Mat.new(8, 9, 2).c()), C.byref(R.Mat.new(8, 9, 1, R.F32).c())) == F.RCV_ERR_SIZE
+    assert F.lib.rcv_yuyv_to_sobel_mag(C.byref(R.Mat.new(8, 8, 3).c()), C.byref(mag.c())) == F.RCV_ERR_DEPTH
+    assert F.lib.rcv_yuyv_to_sobel_mag(C.byref(yuyv.c()), C.byref(R.Mat.new(8, 8, 1).c())) == F.RCV_ERR_DEPTH
+    assert F.lib.rcv_yuyv_to_sobel_mag(C.byref(yuyv.c()), C.byref(mag.c())) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_yuyv_to_bgr_gaussian5(C.byref(yuyv.c()), C.byref(R.Mat.new(8, 8, 3).c())) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_yuyv_to_sobel_mag_batch(None, None, 2) == F.RCV_ERR_ARG
+    assert F.lib.rcv_yuyv_to_sobel_mag_batch(None, None, 0) == F.RCV_OK
+    jpeg = np.frombuffer(b"\xff\xd8\xff\xe0" + bytes(60), np.uint8)
+    w, h = C.c_int32(0), C.c_int32(0)
+    assert F.lib.rcv_mjpeg_info(jpeg.ctypes.data, jpeg.size, C.byref(w), C.byref(h)) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_mjpeg_info(None, 0, C.byref(w), C.byref(h)) == F.RCV_ERR_ARG
+    assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, 2, C.byref(R.Mat.new(8, 8, 3).c())) == F.RCV_ERR_SIZE
+    assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(R.Mat.new(8, 8, 1).c())) == F.RCV_ERR_DEPTH
+    assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(R.Mat.new(8, 8, 3).c())) == F.RCV_ERR_NOT_INIT
