@@ -89,6 +89,10 @@ void orc_sepfilter_u8_q8(const uint8_t *src, size_t sstep, uint8_t *dst,
 void orc_gaussian_blur_u8(const uint8_t *src, size_t sstep, uint8_t *dst,
                           size_t dstep, int rows, int cols, int cn, int kw,
                           int kh, double sigma_x, double sigma_y);
+/* tuned (auto-vectorising) restatement of the 5x5 sigma=0 case; bit-identical, used only as bench.py's second
+ * CPU figure */
+void orc_gauss5_binomial_u8_fast(const uint8_t *src, size_t sstep, uint8_t *dst, size_t dstep, int rows, int cols,
+                                 int cn);
 /* f32 separable: row pass then column pass, fmaf chains in ascending tap order */
 void orc_sepfilter_f32(const float *src, size_t sstep, float *dst, size_t dstep,
                        int rows, int cols, int cn, const float *kx, int kw,

@@ -331,3 +331,17 @@ def test_mjpeg_colour_conversion_formula_is_libjpeg_turbos():
         bgr = np.clip(np.stack([b, gg, r], -1), 0, 255).astype(np.uint8)
         assert (bgr == g[f"bgr_{n}"]).all(), n
         assert (bgr == cv2.imdecode(g[f"jpeg_{n}"], cv2.IMREAD_COLOR)).all(), n
+
+
+def test_tuned_cpu_gaussian_is_bit_identical_to_the_definition(oracle):
+    """oracle.gaussian5_fast (the auto-vectorised restatement bench.py times as its second CPU figure) equals the
+    definition on every geometry class, and reproduces the 4K golden CRC of SURVEY.md section 8c."""
+    for shape in ((5, 5, 3), (7, 9, 1), (64, 83, 3), (33, 40, 4), (1, 1, 3), (2, 3, 3), (3, 1, 2), (120, 301, 3)):
+        a = oracle.fill_u8(1 + shape[0], int(np.prod(shape))).reshape(shape)
+        if shape[2] == 1:
+            a = a.reshape(shape[:2])
+        assert (oracle.gaussian5_fast(a) == oracle.gaussian_blur(a, (5, 5))).all(), shape
+    p = oracle.padded(oracle.fill_u8(13, 33 * 47 * 3).reshape(33, 47, 3), 256)
+    assert (oracle.gaussian5_fast(p) == oracle.gaussian_blur(p, (5, 5))).all()
+    img = oracle.fill_u8(2, 2160 * 3840 * 3).reshape(2160, 3840, 3)
+    assert oracle.crc32(oracle.gaussian5_fast(img)) == 0x827081C8
