@@ -5,16 +5,23 @@
 
 A "step" is one pass of the hot path over one batch of F distinct 4K frames per GPU
 (weak scaling: every rank owns F frames, no data-path collective; the only collective
-is one broadcast of the filter taps before the first launch).
+is one broadcast of the filter taps before the first launch, SURVEY.md section 8e --
+and the taps every rank RECEIVED are the ones its kernel launches with).
 
   value      whole-job Mpix/s, frames resident in HBM, ONE kernel launch per step,
              CUDA events on the library's stream, max over ranks.
+  sustained  the same step looped for >= 2 s with the clock sampler on (the 20-step timed
+             region is a 5 ms burst): frac of the roofline and median SM clock under load.
   e2e        the same metric through the C-ABI batch call with HOST (pinned) Mats:
-             H2D + kernel + D2H inside the timed region.
+             H2D + kernel + D2H inside the timed region; judged against `link_all_ranks`,
+             plain pinned copies of the same bytes run by ALL ranks at the same time.
   roofline   6 algorithmic bytes/pixel (3 read + 3 written) / measured launch time
              against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline  the CPU oracle (a C port of the op's definition; the reference's Rust
-             has no GaussianBlur and no toolchain here) on a bounded sample, rank 0, N=1.
+  extra_configs  BASELINE.json configs 1, 3, 4, 5 and the two fused chains, device-resident,
+             each with its own roofline record and clock sample (cfg4: 256/N frames per rank,
+             cfg5: 64/N).
+  cpu_baseline  the CPU oracle on a bounded sample, rank 0, N=1: the tuned (auto-vectorised,
+             bit-identical) restatement AND the scalar definition port.
 
 `--impl reference` times the CPU arm alone with the same metric/config.
 """
@@ -22,6 +29,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,13 +45,26 @@ ROWS, COLS, CN = 2160, 3840, 3
 PIX = ROWS * COLS
 ALGO_BYTES_PER_PIXEL = 6  # 3 B read + 3 B written
 METRIC = "Mpix/s GaussianBlur 5x5 4K BGR u8"
+WORKLOAD = "GaussianBlur 5x5 sigma=0 REFLECT_101, 3840x2160 BGR u8 (BASELINE.json configs[1])"
 TAPS_Q8 = [16, 64, 96, 64, 16]  # cv::getGaussianKernel(5, 0) * 256
+
+
+def config_dict(world: int, frames: int) -> dict:
+    """The `config` object of the JSON line -- identical for the b200 arm and the reference arm."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames, "launches_per_step_per_gpu": 1,
+            "l2": f"inputs larger than L2: {2 * frames * PIX * CN / 1e6:.0f} MB touched per step vs 126 MB L2",
+            "input": "SplitMix64 seed 2+j per frame", "parallelism": f"frames sharded, {world} rank(s)"}
 
 
 # ---- multi-rank host logic (exercised on gloo by tests/test_dist_gloo.py) ---------------
 def shard_frames(n_frames: int, rank: int, world: int) -> list[int]:
     """frame j -> rank j mod N."""
     return list(range(rank, n_frames, world))
+
+
+def frames_for_rank(total: int, rank: int, world: int) -> int:
+    """How many of a config's `total` frames this rank owns (cfg4: 256, cfg5: 64)."""
+    return len(shard_frames(total, rank, world))
 
 
 def _dist():
@@ -53,7 +74,8 @@ def _dist():
 
 
 def broadcast_taps(taps, device="cuda"):
-    """The one collective of the path: rank 0's filter taps to every rank."""
+    """The one collective of the path: rank 0's filter taps to every rank.  The returned taps
+    are what the caller must launch with."""
     import torch
 
     d = _dist()
@@ -85,6 +107,10 @@ def reduce_sum(x: float, device="cuda") -> float:
     return float(t.item())
 
 
+def reduce_min(x: float, device="cuda") -> float:
+    return -reduce_max(-x, device)
+
+
 def barrier():
     d = _dist()
     if d is not None:
@@ -93,49 +119,51 @@ def barrier():
 
 # ---- clocks -----------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed regions; `window(t0, t1)`
+    summarises the samples taken between two time.time() stamps."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_ms: int = 50):
+        self.index, self.proc, self.samples, self.period_ms = index, None, [], period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", str(self.period_ms)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                rec = (time.time(), float(f[1]), float(f[2]), float(f[3]),
+                       [n for n, v in zip(self.NAMES, f[5:9]) if v.lower().startswith("active")])
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            self.samples.append(rec)
+
+    def window(self, t0: float | None = None, t1: float | None = None) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        s = [r for r in list(self.samples) if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.06)]
+        if not s:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": []}
+        reasons = sorted({n for r in s for n in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in s])), "sm_min_mhz": min(r[1] for r in s),
+                "sm_max_mhz": max(r[2] for r in s), "power_w_max": max(r[3] for r in s), "samples": len(s), "reasons": reasons}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
 
 
 # ---- CPU arm ---------------------------------------------------------------------------------------
@@ -175,41 +203,6 @@ def cpu_gaussian_mpix(frames: int, threads: int, min_seconds: float = 0.0, tuned
     return done * PIX / dt / 1e6, dt, done
 
 
-def pcie_copy_peak(dev, nbytes: int, reps: int = 6) -> dict:
-    """What the link itself gives: plain pinned<->device copies of one e2e step's bytes, each direction alone and
-    both at once on two streams (CUDA events, best of `reps`).  The e2e figure is judged against `duplex_gbs_each`."""
-    import torch
-
-    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-
-    def timed(up: bool, down: bool) -> float:
-        best = 1e30
-        for _ in range(reps):
-            torch.cuda.synchronize(dev)
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            s1.wait_event(e0)
-            s2.wait_event(e0)
-            if up:
-                with torch.cuda.stream(s1):
-                    d_in.copy_(h_in, non_blocking=True)
-            if down:
-                with torch.cuda.stream(s2):
-                    h_out.copy_(d_out, non_blocking=True)
-            e1.record(s1)
-            e2.record(s2)
-            torch.cuda.synchronize(dev)
-            best = min(best, max(e0.elapsed_time(e1), e0.elapsed_time(e2)))
-        return nbytes / (best * 1e-3) / 1e9
-
-    return {"h2d_gbs": timed(True, False), "d2h_gbs": timed(False, True), "duplex_gbs_each": timed(True, True),
-            "bytes_each_way": nbytes}
-
-
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -218,30 +211,37 @@ def host_cores() -> int:
 
 
 def run_reference(args) -> None:
-    """`--impl reference`: the CPU implementation of the path on the host cores.  RustCV
-    has no GaussianBlur and its Rust cannot be built here (no rustc), so this is the
-    oracle port (kind "port"), row-parallel over all host cores.  Rank 0 only."""
+    """`--impl reference`: the CPU implementation of the path on the host cores.  RustCV has no
+    GaussianBlur and its Rust cannot be built here (no rustc), so this is the oracle port (kind
+    "port"), row-parallel over all host cores.  `value` is the TUNED restatement (u16 passes that
+    gcc auto-vectorises, bit-identical to the definition) -- the fair CPU opponent; the scalar
+    definition port is timed beside it.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    frames_per_step = 4
-    arm = CpuArm(cores)
+    frames_per_step = 16
+    arm = CpuArm(cores, tuned=True)
     for _ in range(max(args.warmup, 1)):
-        arm.run(1)
+        arm.run(2)
     secs = 0.0
     for _ in range(args.steps):
         secs += arm.run(frames_per_step)
     mpix = args.steps * frames_per_step * PIX / secs / 1e6
+    slow = CpuArm(cores, tuned=False)
+    slow.run(1)
+    s_secs = slow.run(4)
+    slow_mpix = 4 * PIX / s_secs / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "GaussianBlur 5x5 sigma=0 REFLECT_101, 3840x2160 BGR u8 (BASELINE.json configs[1])",
-                   "frames_per_step": frames_per_step},
+        "config": config_dict(args.gpus, args.frames),
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {frames_per_step} SplitMix64 4K frames, oracle C port "
-                                   f"(RustCV has no GaussianBlur; no rustc here), {cores} row-parallel threads"},
+                         "sample": f"{args.steps} steps x {frames_per_step} SplitMix64 4K frames of the same workload, tuned oracle "
+                                   f"C port (auto-vectorised u16 passes, bit-identical to the definition; RustCV has no "
+                                   f"GaussianBlur and there is no rustc here), {cores} row-parallel threads",
+                         "definition_port": {"value": slow_mpix, "what": f"the scalar definition port, {cores} threads x 4 frames"}},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -266,6 +266,7 @@ def bind_to_gpu_numa_node(local: int) -> str:
         if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit domain
             bus = bus[4:]
         path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        node = open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()
         cpus = set()
         for part in open(path).read().strip().split(","):
             if "-" in part:
@@ -276,10 +277,238 @@ def bind_to_gpu_numa_node(local: int) -> str:
         allowed = cpus & os.sched_getaffinity(0)
         if allowed:
             os.sched_setaffinity(0, allowed)
-            return f"bound to {len(allowed)} CPUs local to {bus}"
+            return f"bound to {len(allowed)} CPUs local to {bus} (numa_node {node})"
         return "unbound (no overlap with the allowed CPU set)"
     except Exception as e:  # noqa: BLE001
         return f"unbound ({e})"
+
+
+# ---- the link ceiling -------------------------------------------------------------------------------
+class LinkProbe:
+    """Plain pinned<->device copies of one e2e step's bytes.  `alone()`: this rank only, each direction and
+    both at once (CUDA events).  `all_ranks()`: EVERY rank runs the duplex copy at the same time, barrier-
+    aligned, wall clock, max over ranks -- the ceiling the e2e figure can be judged against at N > 1."""
+
+    def __init__(self, dev, nbytes: int):
+        import torch
+
+        self.torch, self.dev, self.nbytes = torch, dev, nbytes
+        self.h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.s1, self.s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def _issue(self, up: bool, down: bool):
+        torch = self.torch
+        if up:
+            with torch.cuda.stream(self.s1):
+                self.d_in.copy_(self.h_in, non_blocking=True)
+        if down:
+            with torch.cuda.stream(self.s2):
+                self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def _timed(self, up: bool, down: bool, reps: int) -> float:
+        torch = self.torch
+        best = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize(self.dev)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            self.s1.wait_event(e0)
+            self.s2.wait_event(e0)
+            self._issue(up, down)
+            e1.record(self.s1)
+            e2.record(self.s2)
+            torch.cuda.synchronize(self.dev)
+            best = min(best, max(e0.elapsed_time(e1), e0.elapsed_time(e2)))
+        return self.nbytes / (best * 1e-3) / 1e9
+
+    def alone(self, reps: int = 5) -> dict:
+        return {"h2d_gbs": self._timed(True, False, reps), "d2h_gbs": self._timed(False, True, reps),
+                "duplex_gbs_each": self._timed(True, True, reps), "bytes_each_way": self.nbytes}
+
+    def all_ranks(self, world: int, reps: int = 5) -> dict:
+        torch = self.torch
+        best = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize(self.dev)
+            barrier()
+            t0 = time.perf_counter()
+            self._issue(True, True)
+            torch.cuda.synchronize(self.dev)
+            dt = time.perf_counter() - t0
+            barrier()
+            best = min(best, reduce_max(dt, device=self.dev))  # the slowest rank of this round
+        return {"duplex_gbs_each_total": world * self.nbytes / best / 1e9, "duplex_gbs_each_per_gpu": self.nbytes / best / 1e9,
+                "ranks": world, "bytes_each_way_per_rank": self.nbytes,
+                "how": "all ranks at once, barrier-aligned, wall clock, slowest rank, best of %d" % reps}
+
+
+# ---- BASELINE.json configs 1, 3, 4, 5 and the fused chains, device-resident ----------------------------
+class Extra:
+    def __init__(self, R, O, F, local, rank, world, stream, sampler, peak, min_ms):
+        import torch
+
+        self.R, self.O, self.F, self.torch = R, O, F, torch
+        self.local, self.rank, self.world, self.stream, self.sampler, self.peak, self.min_ms = local, rank, world, stream, sampler, peak, min_ms
+        self.dev = torch.device("cuda", local)
+
+    def fill(self, batch, frames):
+        """frames: list of arrays, cycled over the batch (distinct memory for every frame of the batch)."""
+        import ctypes as C
+
+        hs = [self.R.Mat.from_numpy(a) for a in frames]
+        for i in range(len(batch)):
+            self.F.check(self.F.lib.rcv_mat_upload(C.byref(hs[i % len(hs)].c()), C.byref(batch[i].c())))
+
+    def timeit(self, fn, warm=3):
+        """ms per step (CUDA events on the library stream, max over ranks) over >= min_ms of back-to-back steps."""
+        torch, R = self.torch, self.R
+        for _ in range(warm):
+            fn()
+        R.imgproc.sync(self.local)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        fn()
+        e1.record(self.stream)
+        R.imgproc.sync(self.local)
+        one = max(e0.elapsed_time(e1), 1e-3)
+        steps = max(5, min(4000, int(math.ceil(self.min_ms / one))))
+        barrier()
+        t0 = time.time()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        R.imgproc.sync(self.local)
+        t1 = time.time()
+        ms = reduce_max(e0.elapsed_time(e1) / steps, device=self.dev)
+        return ms, steps, (self.sampler.window(t0, t1) if self.sampler else None)
+
+    def record(self, name, ms, steps, clocks, units_rank, bytes_per_unit, unit, kernel, extra=None):
+        units_all = reduce_sum(float(units_rank), device=self.dev)
+        gbs = units_rank * bytes_per_unit / (ms * 1e-3) / 1e9  # this rank's GPU
+        rec = {"config": name, "n_gpus": self.world, "ms_per_step": ms, "steps": steps, "value": units_all / ms / 1e3,
+               "unit": f"M{unit}/s", "roofline": {"bound": "hbm", "achieved": gbs, "peak": self.peak, "unit": "GB/s",
+                                                   "frac": gbs / self.peak, "algorithmic_bytes_per_unit": bytes_per_unit,
+                                                   "algorithmic_bytes_per_launch": units_rank * bytes_per_unit, "kernel": kernel},
+               "clocks": clocks}
+        rec.update(extra or {})
+        return rec
+
+    def cfg1(self):
+        R, O = self.R, self.O
+        n, h, w = 256, 480, 640
+        src, dst = R.Mat.device_batch(n, h, w, 2), R.Mat.device_batch(n, h, w, 3)
+        base = O.fill_u8(1, h * w * 2)
+        self.fill(src, [np.roll(base, i * 31).reshape(h, w, 2) for i in range(8)])
+        ms, steps, clk = self.timeit(lambda: R.imgproc.cvt_color_batch(src, dst, R.imgproc.COLOR_YUYV2BGR))
+        ok = O.crc32(dst[0].to_numpy()) == 0x0BF66518
+        rec = self.record("cfg1 YUYV->BGR 640x480, 256 frames per launch", ms, steps, clk, n * h * w, 5, "pix", "k_yuv422_vec<0>",
+                          {"parity": {"frame0_crc_0bf66518": ok}})
+        src.free(); dst.free()
+        return rec
+
+    def cfg3(self):
+        R, O = self.R, self.O
+        n, h, w = 64, 1080, 1920
+        src, dst = R.Mat.device_batch(n, h, w, 1, R.F32), R.Mat.device_batch(n, h, w, 1, R.F32)
+        base = O.fill_f32(3, h * w)
+        self.fill(src, [np.roll(base, i * 31).reshape(h, w) for i in range(8)])
+        ms, steps, clk = self.timeit(lambda: R.imgproc.sobel_mag_batch(src, dst))
+        O.set_threads(min(8, host_cores()))
+        want = O.sobel3(base.reshape(h, w))["mag"]
+        O.set_threads(1)
+        got = dst[0].to_numpy()
+        ulp = int(np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max())
+        rec = self.record("cfg3 Sobel3x3+magnitude 1920x1080 f32, 64 frames per launch", ms, steps, clk, n * h * w, 8, "pix",
+                          "k_strip<Sobel3Op<0>>", {"parity": {"frame0_max_ulp_vs_oracle": ulp}})
+        src.free(); dst.free()
+        return rec
+
+    def cfg4(self):
+        R, O = self.R, self.O
+        n, h, w = frames_for_rank(256, self.rank, self.world), 4320, 7680
+        src, dst = R.Mat.device_batch(n, h, w, 3), R.Mat.device_batch(n, h // 4, w // 4, 3)
+        frames = [O.fill_u8(4 + j, h * w * 3).reshape(h, w, 3) for j in shard_frames(256, self.rank, self.world)[:4]]
+        self.fill(src, frames)
+        ms, steps, clk = self.timeit(lambda: R.imgproc.resize_batch(src, dst))
+        ok = (O.crc32(dst[0].to_numpy()) == 0x31A84A85) if self.rank == 0 else None
+        px = n * (h // 4) * (w // 4)
+        rec = self.record(f"cfg4 resize 7680x4320->1920x1080 BGR u8, 256 frames over {self.world} GPU(s)", ms, steps, clk, px, 15,
+                          "dst-pix", "k_resize4x_u8c3",
+                          {"frames_per_gpu": n, "parity": {"frame0_crc_31a84a85": ok},
+                           "sector_floor": {"bytes_per_unit": 27, "frac": px * 27 / (ms * 1e-3) / 1e9 / self.peak,
+                                            "why": "the two source rows of every four are read whole: 32-byte DRAM sectors"},
+                           "distinct_seeds_per_rank": len(frames)})
+        src.free(); dst.free()
+        return rec
+
+    def cfg5(self):
+        R, O = self.R, self.O
+        n, s = frames_for_rank(64, self.rank, self.world), 4096
+        src, dst = R.Mat.device_batch(n, s, s, 1, R.F32), R.Mat.device_batch(n, s, s, 1, R.F32)
+        frames = [O.fill_f32(5 + j, s * s).reshape(s, s) for j in shard_frames(64, self.rank, self.world)[:4]]
+        self.fill(src, frames)
+        M = R.imgproc.get_rotation_matrix_2d(((s - 1) / 2, (s - 1) / 2), 15.0)
+        ms, steps, clk = self.timeit(lambda: R.imgproc.warp_affine_batch(src, dst, M))
+        ulp = None
+        if self.rank == 0:
+            O.set_threads(host_cores())
+            want = O.warp_affine(frames[0], M.ravel())
+            O.set_threads(1)
+            got = dst[0].to_numpy()
+            ulp = int(np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max())
+        rec = self.record(f"cfg5 warpAffine 15deg 4096x4096 f32, 64 frames over {self.world} GPU(s)", ms, steps, clk, n * s * s, 7.6,
+                          "pix", "k_warp_tile<float,1,64>", {"frames_per_gpu": n, "parity": {"frame0_max_ulp_vs_oracle": ulp}})
+        src.free(); dst.free()
+        return rec
+
+    def chain_sobel(self):
+        R, O = self.R, self.O
+        n, h, w = 32, 1080, 1920
+        src, dst = R.Mat.device_batch(n, h, w, 2), R.Mat.device_batch(n, h, w, 1, R.F32)
+        base = O.fill_u8(6, h * w * 2)
+        self.fill(src, [np.roll(base, i * 31).reshape(h, w, 2) for i in range(8)])
+        ms, steps, clk = self.timeit(lambda: R.imgproc.yuyv_to_sobel_mag_batch(src, dst))
+        ok = None
+        if self.rank == 0:
+            O.set_threads(min(8, host_cores()))
+            want = O.sobel3(O.convert_to(O.bgr_to_gray(O.yuyv_to_bgr(base.reshape(h, w, 2))), np.float32))["mag"]
+            O.set_threads(1)
+            ok = bool((dst[0].to_numpy() == want).all())
+        rec = self.record("chain YUYV->BGR->Gray->f32->Sobel magnitude 1920x1080, one fused kernel, 32 frames per launch", ms, steps,
+                          clk, n * h * w, 6, "pix", "k_strip<YuyvSobelOp>", {"parity": {"frame0_bit_exact_vs_oracle_chain": ok}})
+        src.free(); dst.free()
+        return rec
+
+    def chain_gauss(self):
+        R, O = self.R, self.O
+        n, h, w = 32, 2160, 3840
+        src, dst = R.Mat.device_batch(n, h, w, 2), R.Mat.device_batch(n, h, w, 3)
+        base = O.fill_u8(7, h * w * 2)
+        self.fill(src, [np.roll(base, i * 31).reshape(h, w, 2) for i in range(8)])
+        ms, steps, clk = self.timeit(lambda: R.imgproc.yuyv_to_bgr_gaussian5_batch(src, dst))
+        ok = None
+        if self.rank == 0:
+            O.set_threads(min(8, host_cores()))
+            want = O.gaussian_blur(O.yuyv_to_bgr(base.reshape(h, w, 2)), (5, 5))
+            O.set_threads(1)
+            ok = bool((dst[0].to_numpy() == want).all())
+        rec = self.record("chain YUYV->BGR->GaussianBlur5x5 3840x2160, one fused kernel, 32 frames per launch", ms, steps, clk,
+                          n * h * w, 5, "pix", "k_strip<YuyvGauss5Op>", {"parity": {"frame0_bit_exact_vs_oracle_chain": ok}})
+        src.free(); dst.free()
+        return rec
+
+    def run(self, names):
+        out = []
+        for name in names:
+            try:
+                out.append(getattr(self, name)())
+            except Exception as e:  # noqa: BLE001  (one config failing must not lose the headline line)
+                out.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+        return out
 
 
 # ---- GPU arm ---------------------------------------------------------------------------------------
@@ -292,6 +521,14 @@ def main() -> None:
     ap.add_argument("--e2e-frames", type=int, default=32, help="host frames per GPU per e2e step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (configs 1, 3, 4, 5 and the chains)")
+    ap.add_argument("--extra", default="cfg1,cfg3,cfg4,cfg5,chain_sobel,chain_gauss")
+    ap.add_argument("--extra-ms", type=float, default=400.0, help="back-to-back run time per extra config")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="0 = skip the sustained record")
+    ap.add_argument("--no-calls", action="store_true", help="skip the single-call latency records")
+    ap.add_argument("--multi-gpus", type=int, default=0,
+                    help="N=1 only: also run the e2e batch through rcv_gaussian_blur_batch_multi over this many GPUs of the box "
+                         "from this ONE process (the reference's single-caller model)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -317,15 +554,14 @@ def main() -> None:
     import ctypes as C
 
     import rustcv_b200 as R
-    from oracle import pyoracle as O  # input generator (SplitMix64) + cpu_baseline leg only
+    from oracle import pyoracle as O  # input generator (SplitMix64) + cpu_baseline leg + parity checks only
     from rustcv_b200 import _ffi as F
 
     R.imgproc.init(local)
     dev = torch.device("cuda", local)
 
-    # the path's one collective: filter taps from rank 0
-    taps = broadcast_taps(TAPS_Q8 if rank == 0 else None, device=dev)
-    assert taps.tolist() == TAPS_Q8
+    # the path's one collective: filter taps from rank 0; every rank launches with what it received
+    taps = broadcast_taps(TAPS_Q8 if rank == 0 else None, device=dev).astype(np.int32)
 
     # ---- data: F distinct frames per rank, frame j of the job uses seed 2 + j ----------
     F_ = args.frames
@@ -340,8 +576,8 @@ def main() -> None:
     stream = torch.cuda.ExternalStream(R.imgproc.stream_ptr(local), device=dev)
     R.imgproc.set_blocking(False)
 
-    def step():
-        R.imgproc.gaussian_blur_batch(src, dst, (5, 5), 0.0, 0.0)
+    def step():  # the separable-filter entry point with the BROADCAST taps: {16,64,96,64,16} routes to k_strip<Gauss5Op<3>>
+        R.imgproc.sep_filter2d_q8_batch(src, dst, taps, taps)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -355,12 +591,14 @@ def main() -> None:
     launches0 = R.imgproc.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    t_main0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     R.imgproc.sync(local)
     torch.cuda.synchronize()
+    t_main1 = time.time()
     launches = R.imgproc.launch_count() - launches0
     ms_local = e0.elapsed_time(e1)
     barrier()
@@ -369,16 +607,66 @@ def main() -> None:
     total_pix = reduce_sum(float(F_ * PIX), device=dev)  # pixels per step over all ranks
     value = total_pix / (ms_per_step * 1e-3) / 1e6
 
-    # sanity: frame 0 of rank 0 reproduces the golden CRC (seed 2)
+    # sanity: frame 0 of rank 0 reproduces the golden CRC (seed 2), through the taps that were broadcast
     crc_ok = None
     if rank == 0:
         crc_ok = O.crc32(dst[0].to_numpy()) == 0x827081C8
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- sustained: the same step for >= sustained_s seconds, clocks sampled --------------------------
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = int(math.ceil(args.sustained_s * 1e3 / ms_per_step))
+        barrier()
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(n_sus):
+            step()
+        e1.record(stream)
+        R.imgproc.sync(local)
+        t1 = time.time()
+        sus_ms = reduce_max(e0.elapsed_time(e1) / n_sus, device=dev)
+        ach = ALGO_BYTES_PER_PIXEL * F_ * PIX / (sus_ms * 1e-3) / 1e9
+        sustained = {"steps": n_sus, "seconds": n_sus * sus_ms * 1e-3, "ms_per_step": sus_ms,
+                     "value": total_pix / (sus_ms * 1e-3) / 1e6, "achieved": ach, "frac": ach / peak,
+                     "clocks": sampler.window(t0 + 0.2, t1) if rank == 0 else None}
+
+    # ---- single synchronous call on a device-resident Mat (the reference API's own shape) --------------
+    calls = {}
+    if not args.no_calls and rank == 0:
+        s1, d1 = src[0], dst[0]
+        for _ in range(20):
+            R.imgproc.gaussian_blur(s1, d1, (5, 5), 0.0)
+        R.imgproc.sync(local)
+        n_c = 400
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(n_c):
+            R.imgproc.gaussian_blur(src[i % F_], dst[i % F_], (5, 5), 0.0)
+        e1.record(stream)
+        t_enq = time.perf_counter() - t0
+        R.imgproc.sync(local)
+        calls["single_frame_device_call_us"] = e0.elapsed_time(e1) / n_c * 1e3
+        calls["single_frame_device_enqueue_host_us"] = t_enq / n_c * 1e6
+        R.imgproc.set_blocking(True)
+        t0 = time.perf_counter()
+        for i in range(200):
+            R.imgproc.gaussian_blur(src[i % F_], dst[i % F_], (5, 5), 0.0)
+        calls["single_frame_device_blocking_call_us"] = (time.perf_counter() - t0) / 200 * 1e6
+        R.imgproc.set_blocking(False)
+        calls["how"] = ("one 4K frame per rcv_gaussian_blur call, device Mats rotating over 32 frames: GPU time per call from events "
+                        "around 400 back-to-back non-blocking calls; host time per enqueue; wall time of a blocking call")
+
     # ---- e2e: host (pinned) Mats through the public batch call -------------------------
     R.imgproc.set_blocking(True)
     E = args.e2e_frames
-    hsrc = [R.Mat.pinned(ROWS, COLS, CN) for _ in range(E)]
-    hdst = [R.Mat.pinned(ROWS, COLS, CN) for _ in range(E)]
+    hsrc = [R.Mat.pinned(ROWS, COLS, CN, device=local) for _ in range(E)]
+    hdst = [R.Mat.pinned(ROWS, COLS, CN, device=local) for _ in range(E)]
     for i in range(E):
         hsrc[i].data[:] = O.fill_u8(2 + my_frames[i % len(my_frames)], PIX * CN)
 
@@ -389,34 +677,96 @@ def main() -> None:
         e2e_step()
     torch.cuda.synchronize()
     barrier()
+    t_e2e0 = time.time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s_local = time.perf_counter() - t0
+    t_e2e1 = time.time()
     barrier()
     e2e_s = reduce_max(e2e_s_local, device=dev)
     e2e_pix = reduce_sum(float(E * PIX), device=dev)
     e2e_value = e2e_pix * args.steps / e2e_s / 1e6
-    # the reference API's own shape: ONE synchronous call per frame on a pinned host Mat (banded pipeline)
-    for _ in range(3):
-        R.imgproc.gaussian_blur(hsrc[0], hdst[0], (5, 5), 0.0)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        R.imgproc.gaussian_blur(hsrc[0], hdst[0], (5, 5), 0.0)
-    single_ms = (time.perf_counter() - t0) / 20 * 1e3
-    clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up through both timed regions
-    pcie = pcie_copy_peak(dev, E * PIX * CN) if rank == 0 else None  # after the timed regions, outside them
-    e2e_ok = None
+    e2e_ok = (O.crc32(hdst[0].to_numpy()) == 0x827081C8) if rank == 0 else None
+
+    # the link itself: plain pinned copies of the same bytes, all ranks at once, then rank 0 alone
+    probe = LinkProbe(dev, E * PIX * CN)
+    link_all = probe.all_ranks(world)
+    barrier()
+    link_alone = probe.alone() if rank == 0 else None
+    barrier()
+    del probe
+
+    # the reference API's own shape: ONE synchronous call per frame (other ranks idle meanwhile)
+    if not args.no_calls and rank == 0:
+        def wall(fn, n=20, warm=3):
+            for _ in range(warm):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            return (time.perf_counter() - t0) / n * 1e3
+
+        calls["pinned_single_frame_call_ms"] = wall(lambda: R.imgproc.gaussian_blur(hsrc[0], hdst[0], (5, 5), 0.0))
+        # a plain Vec<u8>-like buffer page-locked in place once and reused (videoio/mod.rs:192-199)
+        img = O.fill_u8(2, PIX * CN).reshape(ROWS, COLS, CN)
+        ps, pd = R.Mat.from_numpy(img), R.Mat.new(ROWS, COLS, CN)
+        t0 = time.perf_counter()
+        ps.register(); pd.register()
+        calls["host_register_two_4k_mats_ms"] = (time.perf_counter() - t0) * 1e3
+        calls["registered_pageable_single_frame_call_ms"] = wall(lambda: R.imgproc.gaussian_blur(ps, pd, (5, 5), 0.0))
+        reg_ok = O.crc32(pd.to_numpy()) == 0x827081C8
+        ps.unregister(); pd.unregister()
+        # unregistered pageable memory: the library's bounce ring (memcpy pool + pinned bounce buffers)
+        pd.data[:] = 0
+        calls["pageable_single_frame_call_ms"] = wall(lambda: R.imgproc.gaussian_blur(ps, pd, (5, 5), 0.0))
+        calls["parity"] = {"registered_crc_827081c8": reg_ok, "pageable_crc_827081c8": O.crc32(pd.to_numpy()) == 0x827081C8}
+        # fresh destination buffer every call (first touch inside the call)
+        def fresh():
+            d = R.Mat.new(ROWS, COLS, CN)
+            R.imgproc.gaussian_blur(ps, d, (5, 5), 0.0)
+        calls["pageable_fresh_dst_single_frame_call_ms"] = wall(fresh, n=10)
+    barrier()
+
+    # ---- one process, several GPUs: the in-library fan-out (opt-in; the driver's runs leave it off) ----
+    multi = None
+    if args.multi_gpus > 1 and world == 1:
+        g = args.multi_gpus
+        R.imgproc.init_multi(g)
+        msrc = [R.Mat.pinned(ROWS, COLS, CN, device=i % g) for i in range(E * g)]
+        mdst = [R.Mat.pinned(ROWS, COLS, CN, device=i % g) for i in range(E * g)]
+        for i in range(E * g):
+            msrc[i].data[:] = hsrc[i % E].data
+        for _ in range(2):
+            R.imgproc.gaussian_blur_batch_multi(msrc, mdst, g, (5, 5), 0.0, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            R.imgproc.gaussian_blur_batch_multi(msrc, mdst, g, (5, 5), 0.0, 0.0)
+        dt = time.perf_counter() - t0
+        mv = E * g * PIX * args.steps / dt / 1e6
+        multi = {"ngpus": g, "value": mv, "unit": "Mpix/s", "frames_per_step": E * g, "gbs_each_way_total": mv * 1e6 * CN / 1e9,
+                 "api": "rcv_gaussian_blur_batch_multi, ONE calling thread, frame j -> GPU j mod N",
+                 "parity_last_frame_crc": O.crc32(mdst[E * g - 1].to_numpy()) == O.crc32(hdst[(E * g - 1) % E].to_numpy())}
+        del msrc, mdst
+
+    clocks = sampler.window(t_main0 - 0.05, t_main1) if rank == 0 else None
+    clocks_e2e = sampler.window(t_e2e0, t_e2e1) if rank == 0 else None
+    del hsrc, hdst
+    src.free(); dst.free()
+
+    # ---- the other BASELINE.json configs, same process, each with roofline + clocks --------------------------
+    extra = None
+    R.imgproc.set_blocking(False)
+    if not args.no_extra:
+        ex = Extra(R, O, F, local, rank, world, stream, sampler if rank == 0 else None, peak, args.extra_ms)
+        extra = ex.run([n for n in args.extra.split(",") if n])
+    R.imgproc.set_blocking(True)
     if rank == 0:
-        e2e_ok = O.crc32(hdst[0].to_numpy()) == 0x827081C8
+        all_clocks = sampler.window()
+        sampler.stop()
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         # one launch per step on every rank: per-launch time = ms_per_step
         achieved = ALGO_BYTES_PER_PIXEL * F_ * PIX / (ms_per_step * 1e-3) / 1e9
         traffic = None
@@ -425,45 +775,48 @@ def main() -> None:
             tj = json.load(open(tpath))
             if tj.get("frames_per_launch") == F_:
                 traffic = tj.get("dram_bytes_per_launch")
+        each_way = e2e_value * 1e6 * CN / 1e9  # GB/s each way, all ranks together
+        if clocks and (clocks.get("samples") or 0) == 0:
+            clocks = all_clocks  # the 5 ms burst fell between two samples: report the run's
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "GaussianBlur 5x5 sigma=0 REFLECT_101, 3840x2160 BGR u8 (BASELINE.json configs[1])",
-                       "frames_per_gpu_per_step": F_, "launches_per_step_per_gpu": 1,
-                       "l2": f"inputs larger than L2: {2 * F_ * PIX * CN / 1e6:.0f} MB touched per step vs 126 MB L2",
-                       "input": "SplitMix64 seed 2+j per frame", "parallelism": f"frames sharded, {world} rank(s)"},
+            "config": config_dict(world, F_),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_strip<Gauss5Op<3>>",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * F_ * PIX},
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * F_ * PIX, "sustained": sustained},
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": E * PIX * CN * world,
                     "d2h_bytes_per_step": E * PIX * CN * world, "frames_per_gpu_per_step": E,
-                    "api": "rcv_gaussian_blur_batch on pinned host Mats", "host_binding": numa,
-                    "single_frame_call_ms": single_ms,
-                    "link": pcie,
-                    "achieved_gbs_each_way": e2e_value * 1e6 * CN / 1e9 / world,
-                    "frac_of_duplex_copy": (e2e_value * 1e6 * CN / 1e9 / world) / pcie["duplex_gbs_each"]},
+                    "api": "rcv_gaussian_blur_batch on pinned host Mats (rcv_pinned_alloc_on)", "host_binding": numa,
+                    "achieved_gbs_each_way_total": each_way, "achieved_gbs_each_way_per_gpu": each_way / world,
+                    "link_all_ranks": link_all, "frac_of_link_all_ranks": each_way / link_all["duplex_gbs_each_total"],
+                    "link_rank0_alone": link_alone,
+                    "one_process_multi_gpu": multi, "clocks": clocks_e2e},
+            "calls": calls or None,
+            "collective": {"what": "broadcast of the 5 Q8 filter taps from rank 0 (NCCL)" if world > 1 else "none at N=1 (taps are local)",
+                           "taps_received": taps.tolist(), "consumed_by": "rcv_sep_filter2d_q8_batch(taps) -> k_strip<Gauss5Op<3>>"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "clocks_whole_run": all_clocks,
             "parity": {"device_frame0_crc_827081c8": crc_ok, "e2e_frame0_crc_827081c8": e2e_ok},
+            "extra_configs": extra,
         }
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again
             cores = host_cores()
-            v_all, s_all, n_all = cpu_gaussian_mpix(16 if cores >= 8 else 4, cores, min_seconds=8.0)
-            v_one, s_one, n_one = cpu_gaussian_mpix(4, 1, min_seconds=4.0)
-            t_all, ts_all, tn_all = cpu_gaussian_mpix(16, cores, min_seconds=3.0, tuned=True)
-            t_one, ts_one, tn_one = cpu_gaussian_mpix(8, 1, min_seconds=2.0, tuned=True)
-            line["cpu_baseline"] = {"value": v_all, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                    "tuned_port": {"value": t_all, "value_1_thread": t_one, "cores": cores,
-                                                   "what": "the same result from an auto-vectorised restatement "
-                                                           "(u16 vertical pass, branch-free horizontal pass; "
-                                                           f"bit-identical, gcc -O3, no -march): {tn_all} frames in "
-                                                           f"{ts_all:.1f} s; not the definition, reported so the CPU "
-                                                           "figure is not an artefact of scalar code"},
-                                    "sample": f"oracle C port, {cores} threads x {n_all} frames of the same workload "
-                                              f"({s_all:.1f} s); 1 thread x {n_one} frames = {v_one:.0f} Mpix/s ({s_one:.1f} s)",
-                                    "value_1_thread": v_one}
+            t_all, ts_all, tn_all = cpu_gaussian_mpix(16, cores, min_seconds=6.0, tuned=True)
+            t_one, ts_one, tn_one = cpu_gaussian_mpix(8, 1, min_seconds=3.0, tuned=True)
+            v_all, s_all, n_all = cpu_gaussian_mpix(16 if cores >= 8 else 4, cores, min_seconds=6.0)
+            v_one, s_one, n_one = cpu_gaussian_mpix(4, 1, min_seconds=3.0)
+            line["cpu_baseline"] = {
+                "value": t_all, "unit": "Mpix/s", "cores": cores, "kind": "port", "value_1_thread": t_one,
+                "sample": f"tuned oracle C port (u16 vertical pass, branch-free horizontal pass that gcc -O3 auto-vectorises; "
+                          f"bit-identical to the definition), {cores} threads x {tn_all} frames of the same workload ({ts_all:.1f} s); "
+                          f"1 thread x {tn_one} frames ({ts_one:.1f} s)",
+                "definition_port": {"value": v_all, "value_1_thread": v_one, "cores": cores,
+                                    "sample": f"the scalar definition (oracle/rcv_oracle.c orc_gaussian_blur_u8), {cores} threads x "
+                                              f"{n_all} frames ({s_all:.1f} s); 1 thread x {n_one} frames ({s_one:.1f} s)"}}
         print(json.dumps(line), flush=True)
 
     if world > 1:

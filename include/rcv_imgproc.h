@@ -20,6 +20,10 @@
  * rcv_set_blocking(0) was called, re-entrant, and thread-safe for distinct
  * Mats.  One CUDA context per GPU; work for a Mat runs on the GPU named by
  * RcvMat.device (device Mats) or on the GPU given to rcv_init (host Mats).
+ * The *_batch_multi calls fan a batch out over several GPUs from the ONE
+ * calling thread (the reference API is a single synchronous caller,
+ * README.md:31, rustcv/src/videoio/mod.rs:168): the library owns one worker
+ * thread per GPU and returns when every frame is done.
  *
  * There is NO CPU fallback: without a B200-class GPU rcv_init returns
  * RCV_ERR_CUDA and every op returns RCV_ERR_NOT_INIT.
@@ -49,6 +53,7 @@ extern "C" {
 #define RCV_ERR_UNSUPPORTED (-5) /* valid request this build does not cover   */
 #define RCV_ERR_NOT_INIT (-6)    /* rcv_init has not succeeded                */
 #define RCV_ERR_NOMEM (-7)       /* device or pinned allocation failed        */
+#define RCV_ERR_NCCL (-8)        /* the coefficient broadcast failed (NCCL)   */
 
 /* ---- Mat --------------------------------------------------------------- */
 /* depth tag: rustcv::core::Mat is u8-only (rustcv/src/core/mat.rs:6-15, TODO
@@ -83,6 +88,10 @@ typedef struct RcvMat {
  * the default device for host Mats.  Fails with RCV_ERR_CUDA when the GPU is
  * not compute capability 10.x. */
 RCV_API int rcv_init(int device);
+/* rcv_init for GPUs 0..ngpus-1 (ngpus <= 0: every GPU of the box) and one
+ * worker thread per GPU, bound to the CPUs local to it.  rcv_init(-1) binds
+ * to the GPU named by the environment variable RCV_DEVICE (default 0). */
+RCV_API int rcv_init_multi(int32_t ngpus);
 RCV_API int rcv_shutdown(void);
 RCV_API int rcv_device_count(int *count);
 /* 1 (default): every op returns after its work completed.  0: ops on device
@@ -111,7 +120,20 @@ RCV_API int rcv_mat_free_device_batch(RcvMat *mats, int32_t n);
 RCV_API int rcv_mat_upload(const RcvMat *host, RcvMat *dev);
 RCV_API int rcv_mat_download(const RcvMat *dev, RcvMat *host);
 RCV_API int rcv_pinned_alloc(void **ptr, size_t bytes);
+/* The same, with the pages placed on the NUMA node of GPU `device` (the GPU
+ * that will DMA them) when the box exposes several nodes; device < 0 = the
+ * default GPU.  Free with rcv_pinned_free. */
+RCV_API int rcv_pinned_alloc_on(int32_t device, void **ptr, size_t bytes);
 RCV_API int rcv_pinned_free(void *ptr);
+/* Page-locks a CALLER-OWNED buffer in place -- the Vec<u8> behind a reference
+ * Mat, which read() reuses frame after frame (rustcv/src/videoio/mod.rs:192-199,
+ * rustcv-camera/src/mat.rs:65-74).  Afterwards an RCV_HOST Mat inside the range
+ * is DMA'd directly, like RCV_HOST_PINNED.  The caller must unregister before
+ * freeing or reallocating the buffer (the Rust wrapper does so in Drop and in
+ * ensure_size).  Unregistered pageable Mats still work: they go
+ * through the library's pinned bounce ring. */
+RCV_API int rcv_host_register(void *ptr, size_t bytes);
+RCV_API int rcv_host_unregister(void *ptr);
 
 /* ---- pixel-format conversion (cvtColor) ---------------------------------
  * The reference's own hot loops: rustcv/src/videoio/mod.rs:344-399, twins in
@@ -201,6 +223,37 @@ RCV_API int rcv_warp_affine_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, c
 RCV_API int rcv_cvt_color_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t code);
 RCV_API int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs_yuyv, RcvMat *mags_f32, int32_t n);
 RCV_API int rcv_yuyv_to_bgr_gaussian5_batch(const RcvMat *srcs_yuyv, RcvMat *dsts_bgr, int32_t n);
+RCV_API int rcv_sep_filter2d_q8_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const int32_t *kx, int32_t kw,
+                              const int32_t *ky, int32_t kh);
+
+/* ---- the same batches sharded over several GPUs -----
+ * Frames are independent: host Mats go frame j -> GPU j mod ngpus, device Mats
+ * run on the GPU that owns them (src and dst of a frame on the same GPU).
+ * ngpus <= 0: every initialised GPU (rcv_init_multi).  Each GPU runs its share
+ * on its own worker thread, streams and staging ring; there is no inter-GPU
+ * traffic on the pixel path.  Returns the first failing frame's code. */
+RCV_API int rcv_gaussian_blur_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus, int32_t kw,
+                                  int32_t kh, double sigma_x, double sigma_y);
+RCV_API int rcv_sobel_mag_batch_multi(const RcvMat *srcs, RcvMat *mags, int32_t n, int32_t ngpus);
+RCV_API int rcv_resize_bilinear_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus);
+RCV_API int rcv_warp_affine_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus, const double M[6],
+                                int32_t inverse_map, double border_value);
+RCV_API int rcv_cvt_color_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus, int32_t code);
+RCV_API int rcv_yuyv_to_sobel_mag_batch_multi(const RcvMat *srcs_yuyv, RcvMat *mags_f32, int32_t n, int32_t ngpus);
+RCV_API int rcv_yuyv_to_bgr_gaussian5_batch_multi(const RcvMat *srcs_yuyv, RcvMat *dsts_bgr, int32_t n, int32_t ngpus);
+/* kx == NULL and ky == NULL: every GPU filters with the taps IT received from
+ * rcv_set_kernel_broadcast (kw taps for x, then kh taps for y). */
+RCV_API int rcv_sep_filter2d_q8_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus,
+                                    const int32_t *kx, int32_t kw, const int32_t *ky, int32_t kh);
+
+/* The path's single collective: filter coefficients are set up once, on GPU
+ * `root_device`, and broadcast (ncclBroadcast over NVLink) into the coefficient
+ * bank of the other initialised GPUs (ngpus <= 0: all).  `coeffs`: count <=
+ * RCV_COEFF_BANK_MAX f32 values.  `received` (optional, ngpus x count floats)
+ * returns each GPU's copy, read back from its bank.  RCV_ERR_NCCL on failure. */
+#define RCV_COEFF_BANK_MAX 64
+RCV_API int rcv_set_kernel_broadcast(const float *coeffs, int32_t count, int32_t root_device, int32_t ngpus,
+                             float *received);
 
 /* ---- tuning knobs (benchmark/diagnostic use) ----------------------------- */
 /* name/value integer options, e.g. "gauss.band_rows", "gauss.variant". */

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RCV_IMGPROC_LIB") or os.path.join(_HERE, "librcv_imgp
 
 RCV_OK = 0
 RCV_ERR_ARG, RCV_ERR_SIZE, RCV_ERR_DEPTH, RCV_ERR_CUDA = -1, -2, -3, -4
-RCV_ERR_UNSUPPORTED, RCV_ERR_NOT_INIT, RCV_ERR_NOMEM = -5, -6, -7
+RCV_ERR_UNSUPPORTED, RCV_ERR_NOT_INIT, RCV_ERR_NOMEM, RCV_ERR_NCCL = -5, -6, -7, -8
 RCV_U8, RCV_F32 = 0, 1
 RCV_HOST, RCV_DEVICE, RCV_HOST_PINNED = 0, 1, 2
 
@@ -50,6 +50,7 @@ _MatP = _P(RcvMat)
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 SIGNATURES = {
     "rcv_init": [C.c_int],
+    "rcv_init_multi": [C.c_int32],
     "rcv_shutdown": [],
     "rcv_device_count": [_P(C.c_int)],
     "rcv_set_blocking": [C.c_int],
@@ -65,7 +66,10 @@ SIGNATURES = {
     "rcv_mat_upload": [_MatP, _MatP],
     "rcv_mat_download": [_MatP, _MatP],
     "rcv_pinned_alloc": [_P(C.c_void_p), C.c_size_t],
+    "rcv_pinned_alloc_on": [C.c_int32, _P(C.c_void_p), C.c_size_t],
     "rcv_pinned_free": [C.c_void_p],
+    "rcv_host_register": [C.c_void_p, C.c_size_t],
+    "rcv_host_unregister": [C.c_void_p],
     "rcv_cvt_color": [_MatP, _MatP, C.c_int32],
     "rcv_yuyv_to_bgr": [_MatP, _MatP],
     "rcv_yuyv_to_bgr_packed": [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t],
@@ -92,6 +96,17 @@ SIGNATURES = {
     "rcv_resize_bilinear_batch": [_MatP, _MatP, C.c_int32],
     "rcv_warp_affine_batch": [_MatP, _MatP, C.c_int32, _P(C.c_double), C.c_int32, C.c_double],
     "rcv_cvt_color_batch": [_MatP, _MatP, C.c_int32, C.c_int32],
+    "rcv_sep_filter2d_q8_batch": [_MatP, _MatP, C.c_int32, _P(C.c_int32), C.c_int32, _P(C.c_int32), C.c_int32],
+    "rcv_gaussian_blur_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double],
+    "rcv_sobel_mag_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],
+    "rcv_resize_bilinear_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],
+    "rcv_warp_affine_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, _P(C.c_double), C.c_int32, C.c_double],
+    "rcv_cvt_color_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_int32],
+    "rcv_yuyv_to_sobel_mag_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],
+    "rcv_yuyv_to_bgr_gaussian5_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],
+    "rcv_sep_filter2d_q8_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, _P(C.c_int32), C.c_int32, _P(C.c_int32),
+                                        C.c_int32],
+    "rcv_set_kernel_broadcast": [_P(C.c_float), C.c_int32, C.c_int32, C.c_int32, _P(C.c_float)],
     "rcv_set_option": [C.c_char_p, C.c_int64],
     "rcv_get_option": [C.c_char_p, _P(C.c_int64)],
 }

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -52,6 +53,8 @@ static std::mutex g_mu;
 static std::atomic<int> g_blocking{1};
 static std::atomic<uint64_t> g_launches{0};
 static std::map<std::string, int64_t> g_opts;
+static std::mutex g_opt_mu;
+static std::atomic<int> g_opts_set{0};  // no option was ever set (every production call): opt_get takes no lock
 
 Ctx *ctx_get(int device) {
   if (device < 0 || device >= kMaxDevices || !g_ctx[device]) {
@@ -74,7 +77,8 @@ bool ctx_blocking() { return g_blocking.load() != 0; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
 
 int64_t opt_get(const char *name, int64_t dflt) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_opts_set.load(std::memory_order_acquire) == 0) return dflt;
+  std::lock_guard<std::mutex> lk(g_opt_mu);
   auto it = g_opts.find(name);
   return it == g_opts.end() ? dflt : it->second;
 }
@@ -93,6 +97,41 @@ int ctx_scratch(Ctx *c, int slot, size_t bytes, void **ptr) {
     if (slot == SCR_TABLE_X || slot == SCR_TABLE_Y) memset(c->resize_key, 0, sizeof(c->resize_key));
   }
   *ptr = c->scratch[slot];
+  return RCV_OK;
+}
+
+int devices_initialised(int *out, int cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int n = 0;
+  for (int d = 0; d < kMaxDevices && n < cap; ++d)
+    if (g_ctx[d]) out[n++] = d;
+  return n;
+}
+
+int ctx_tmap_rows_u32(Ctx *c, const CUtensorMap **out, const void *base, size_t row_bytes, int rows, size_t step, int n,
+                      size_t frame_stride, int box_w_words, int box_h) {
+  Ctx::TmapEntry *victim = &c->tmaps[0];
+  for (int i = 0; i < kTmapCache; ++i) {
+    Ctx::TmapEntry &e = c->tmaps[i];
+    if (e.base == base && e.row_bytes == row_bytes && e.rows == rows && e.step == step && e.n == n &&
+        e.frame_stride == frame_stride && e.box_w == box_w_words && e.box_h == box_h) {
+      e.stamp = ++c->tmap_clock;
+      *out = &e.map;
+      return RCV_OK;
+    }
+    if (e.stamp < victim->stamp) victim = &e;
+  }
+  RCV_TRY(make_tmap_rows_u32(&victim->map, base, row_bytes, rows, step, n, frame_stride, box_w_words, box_h));
+  victim->base = base;
+  victim->row_bytes = row_bytes;
+  victim->rows = rows;
+  victim->step = step;
+  victim->n = n;
+  victim->frame_stride = frame_stride;
+  victim->box_w = box_w_words;
+  victim->box_h = box_h;
+  victim->stamp = ++c->tmap_clock;
+  *out = &victim->map;
   return RCV_OK;
 }
 
@@ -118,10 +157,16 @@ static int ctx_create(int device) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
+    c->out_pending[i].store(0);
+    for (int b = 0; b < kMaxBands && e == cudaSuccess; ++b)
+      e = cudaEventCreateWithFlags(&c->ev_band[i][b], cudaEventDisableTiming | cudaEventBlockingSync);
+  }
   if (e != cudaSuccess) {
     delete c;
     return cuda_fail(e, "stream/event creation");
   }
+  c->numa_node = gpu_numa_node(device);
   g_ctx[device] = c;
   if (g_default_device < 0) g_default_device = device;
   return RCV_OK;
@@ -134,21 +179,38 @@ using namespace rcv;
 extern "C" {
 
 int rcv_init(int device) {
+  // device < 0: the ordinal named by the environment variable RCV_DEVICE, else GPU 0 -- the library's one
+  // piece of run-time configuration; like the reference there is no runtime backend dispatch
+  // (rustcv/src/videoio/backend.rs:13-37 selects its backend at compile time).
+  if (device < 0) {
+    const char *env = getenv("RCV_DEVICE");
+    device = (env && *env) ? atoi(env) : 0;
+  }
   std::lock_guard<std::mutex> lk(g_mu);
   if (device >= 0 && device < kMaxDevices && g_ctx[device]) return RCV_OK;
   return ctx_create(device);
 }
 
 int rcv_shutdown(void) {
+  multi_shutdown();  // workers first: none may hold a context while it is torn down
+  drain_shutdown();
   std::lock_guard<std::mutex> lk(g_mu);
   for (int d = 0; d < kMaxDevices; ++d) {
     Ctx *c = g_ctx[d];
     if (!c) continue;
     cudaSetDevice(d);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_out);
     jpeg_destroy(c);
     for (int i = 0; i < SCR_COUNT; ++i)
       if (c->scratch[i]) cudaFree(c->scratch[i]);
+    for (int i = 0; i < kRing; ++i) {
+      if (c->bounce_in[i]) cudaFreeHost(c->bounce_in[i]);
+      if (c->bounce_out[i]) cudaFreeHost(c->bounce_out[i]);
+      for (int b = 0; b < kMaxBands; ++b) cudaEventDestroy(c->ev_band[i][b]);
+    }
+    if (c->coeff_bank) cudaFree(c->coeff_bank);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->s_in);
     cudaStreamDestroy(c->s_out);
@@ -161,6 +223,8 @@ int rcv_shutdown(void) {
     g_ctx[d] = nullptr;
   }
   g_default_device = -1;
+  host_registry_shutdown();
+  cudaGetLastError();
   return RCV_OK;
 }
 
@@ -198,34 +262,22 @@ int rcv_launch_count(uint64_t *count) {
 
 const char *rcv_last_error(void) { return rcv::last_error(); }
 
-const char *rcv_version(void) { return "rcv_imgproc 0.1 (sm_100a)"; }
+const char *rcv_version(void) { return "rcv_imgproc 0.2 (sm_100a)"; }
 
 int rcv_set_option(const char *name, int64_t value) {
   if (!name) return fail(RCV_ERR_ARG, "name is NULL");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_opt_mu);
   g_opts[name] = value;
+  g_opts_set.store(1, std::memory_order_release);
   return RCV_OK;
 }
 
 int rcv_get_option(const char *name, int64_t *value) {
   if (!name || !value) return fail(RCV_ERR_ARG, "NULL argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_opt_mu);
   auto it = g_opts.find(name);
   if (it == g_opts.end()) return fail(RCV_ERR_ARG, "option %s is not set", name);
   *value = it->second;
-  return RCV_OK;
-}
-
-int rcv_pinned_alloc(void **ptr, size_t bytes) {
-  if (!ptr) return fail(RCV_ERR_ARG, "ptr is NULL");
-  if (!ctx_default()) return RCV_ERR_NOT_INIT;
-  RCV_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
-  return RCV_OK;
-}
-
-int rcv_pinned_free(void *ptr) {
-  if (!ptr) return RCV_OK;
-  RCV_CUDA(cudaFreeHost(ptr));
   return RCV_OK;
 }
 

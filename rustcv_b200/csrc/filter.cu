@@ -167,8 +167,42 @@ static int launch_sep(const DBatch &src, const DBatch &dst, const typename SepTr
   return RCV_OK;
 }
 
-int launch_sepfilter_q8(Ctx *, const DBatch &src, const DBatch &dst, const int32_t *kx, int kw, const int32_t *ky,
+int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_gauss3_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
+int launch_gaussq8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, const int32_t *ky, int ks,
+                         cudaStream_t s);
+
+// Symmetric non-negative taps summing to 256: the vertical sums fit 16-bit lanes, which is what the strip ops
+// (and nothing else about a Gaussian) rely on.
+static bool strip_taps_ok(const int32_t *k, int n) {
+  int sum = 0;
+  for (int i = 0; i < n; ++i) {
+    if (k[i] < 0 || k[i] != k[n - 1 - i]) return false;
+    sum += k[i];
+  }
+  return sum == 256;
+}
+
+// u8 separable filter with Q8 taps: the TMA strip ops when the taps allow it (5x5 / 3x3 binomial have their own
+// ops, any other symmetric 3 / 5 / 7 taps GaussQ8Op), else the general kernel.
+int launch_sepfilter_q8(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, int kw, const int32_t *ky,
                         int kh, cudaStream_t s) {
+  if (kw == kh && (kw == 3 || kw == 5 || kw == 7) && opt_get("gauss.force_generic", 0) == 0 && strip_taps_ok(kx, kw) &&
+      strip_taps_ok(ky, kh) && src.v.rows > 0 && src.v.cols > 0 && src.n > 0) {
+    const bool binomial5 = kw == 5 && kx[0] == 16 && kx[1] == 64 && kx[2] == 96 && ky[0] == 16 && ky[1] == 64 && ky[2] == 96;
+    if (binomial5) {
+      int rc = launch_gauss5_strip(c, src, dst, s);
+      if (rc != RCV_ERR_UNSUPPORTED) return rc;
+    }
+    const bool binomial3 = kw == 3 && kx[0] == 64 && kx[1] == 128 && ky[0] == 64 && ky[1] == 128;
+    if (binomial3 && opt_get("gauss.no_binomial3", 0) == 0) {
+      int rc = launch_gauss3_strip(c, src, dst, s);
+      if (rc != RCV_ERR_UNSUPPORTED) return rc;
+    }
+    int rc = launch_gaussq8_strip(c, src, dst, kx, ky, kw, s);
+    if (rc != RCV_ERR_UNSUPPORTED) return rc;
+  }
+  if (dst.windowed()) return RCV_ERR_UNSUPPORTED;  // whole-image kernel: the caller retries without a row window
   return launch_sep<uint8_t>(src, dst, kx, kw, ky, kh, s);
 }
 
@@ -235,11 +269,6 @@ void gaussian_kernel_q8(int n, double sigma, int32_t *kq) {
   kq[n2] = 256 - 2 * sum;
 }
 
-int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
-int launch_gauss3_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
-int launch_gaussq8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, const int32_t *ky, int ks,
-                         cudaStream_t s);
-
 int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh, double sx, double sy,
                     cudaStream_t s) {
   const bool u8 = src.v.depth == RCV_U8;
@@ -252,22 +281,6 @@ int launch_gaussian(Ctx *c, const DBatch &src, const DBatch &dst, int kw, int kh
     int32_t kx[kMaxTaps + 1], ky[kMaxTaps + 1];
     gaussian_kernel_q8(kw, sx, kx);
     gaussian_kernel_q8(kh, sy, ky);
-    const bool binomial5 = kw == 5 && kh == 5 && kx[0] == 16 && kx[1] == 64 && kx[2] == 96 && ky[0] == 16 &&
-                           ky[1] == 64 && ky[2] == 96;
-    if (binomial5 && opt_get("gauss.force_generic", 0) == 0) {
-      int rc = launch_gauss5_strip(c, src, dst, s);
-      if (rc != RCV_ERR_UNSUPPORTED) return rc;
-    }
-    const bool binomial3 = kw == 3 && kh == 3 && kx[0] == 64 && kx[1] == 128 && ky[0] == 64 && ky[1] == 128;
-    if (binomial3 && opt_get("gauss.force_generic", 0) == 0 && opt_get("gauss.no_binomial3", 0) == 0) {
-      int rc = launch_gauss3_strip(c, src, dst, s);
-      if (rc != RCV_ERR_UNSUPPORTED) return rc;
-    }
-    if (kw == kh && (kw == 3 || kw == 5 || kw == 7) && opt_get("gauss.force_generic", 0) == 0) {
-      int rc = launch_gaussq8_strip(c, src, dst, kx, ky, kw, s);
-      if (rc != RCV_ERR_UNSUPPORTED) return rc;
-    }
-    if (dst.windowed()) return RCV_ERR_UNSUPPORTED;
     return launch_sepfilter_q8(c, src, dst, kx, kw, ky, kh, s);
   }
   double kd[kMaxTaps + 1];

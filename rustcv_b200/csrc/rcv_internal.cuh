@@ -8,6 +8,10 @@
 //   filter.cu    generic separable / dense filters (u8 Q8, f32)
 //   geom.cu      bilinear resize, warpAffine
 //   mjpeg.cu     the MJPEG branch of read() through nvJPEG (library decoder)
+//   hostmem.cu   host-side memory: NUMA-placed pinned allocations, the registration cache for caller-owned
+//                Vec<u8> buffers, the parallel memcpy pool behind the pageable bounce pipeline
+//   multi.cu     one worker thread per GPU (frame j -> GPU j mod N inside ONE caller process), the NCCL
+//                broadcast of filter coefficients
 //   abi.cu       the extern "C" entry points of include/rcv_imgproc.h
 #pragma once
 
@@ -16,7 +20,9 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <atomic>
 #include <mutex>
+#include <set>
 
 #include "../../include/rcv_imgproc.h"
 
@@ -65,7 +71,9 @@ struct DBatch {
 };
 
 // ---- context ----------------------------------------------------------------
-constexpr int kRing = 4;  // staging ring depth for host-resident batches
+constexpr int kRing = 4;       // staging ring depth for host-resident batches
+constexpr int kMaxBands = 32;  // row bands per frame in the pageable bounce pipeline (one event each)
+constexpr int kTmapCache = 8;  // tensor maps remembered per context (one per recent (base, geometry))
 
 enum ScratchSlot {
   SCR_STAGE_IN0 = 0,   // + slot            (kRing staged inputs; NV12 uses slot 1 for the UV plane)
@@ -92,6 +100,29 @@ struct Ctx {
   unsigned counter_parity = 0;       // which of the two strip-kernel work counters the next launch uses
   int resize_key[4] = {0, 0, 0, 0};  // geometry of the resize tables currently in SCR_TABLE_X/Y
   void *jpeg = nullptr;              // nvJPEG handle + state of the MJPEG branch (mjpeg.cu), created on first use
+  // pinned bounce buffers of the pageable pipeline (abi.cu): one whole-frame buffer per ring slot and side,
+  // grown on demand; ev_band[k][b] marks "band b of slot k has landed in bounce_out[k]".
+  void *bounce_in[kRing] = {}, *bounce_out[kRing] = {};
+  size_t bounce_in_bytes[kRing] = {}, bounce_out_bytes[kRing] = {};
+  cudaEvent_t ev_band[kRing][kMaxBands] = {};
+  // CUtensorMap cache: encoding a map costs a driver call per launch; the reference API is one call per frame
+  // on the SAME reused buffers (rustcv/src/videoio/mod.rs:192-199), so the map of the last few
+  // (base, geometry) pairs is kept.
+  struct TmapEntry {
+    const void *base = nullptr;
+    size_t row_bytes = 0, step = 0, frame_stride = 0;
+    int rows = 0, n = 0, box_w = 0, box_h = 0;
+    uint64_t stamp = 0;
+    CUtensorMap map;
+  } tmaps[kTmapCache];
+  uint64_t tmap_clock = 0;
+  int numa_node = -1;                // NUMA node of the GPU (sysfs), -1 unknown / single node
+  float *coeff_bank = nullptr;       // device copy of the broadcast filter coefficients (multi.cu)
+  float coeffs[RCV_COEFF_BANK_MAX] = {};  // what this GPU received (read back from ITS bank after the broadcast)
+  int n_coeffs = 0;
+  std::atomic<int> out_pending[kRing];    // bounce_out[k] bands not yet copied to their Mat by the drain thread
+  std::atomic<int> drain_failed{0};
+  std::set<void *> dev_allocs;            // bases returned by rcv_mat_alloc_device[_batch] (what cudaFree may take)
   std::mutex mu;
 };
 
@@ -112,6 +143,44 @@ int ctx_scratch(Ctx *c, int slot, size_t bytes, void **ptr);
 // dims {ceil(row_bytes/4), rows, n}, strides {step, frame_stride}, box {box_w, box_h, 1}.
 int make_tmap_rows_u32(CUtensorMap *out, const void *base, size_t row_bytes, int rows, size_t step, int n,
                        size_t frame_stride, int box_w_words, int box_h);
+// the same through the context's cache (c->mu held by the caller)
+int ctx_tmap_rows_u32(Ctx *c, const CUtensorMap **out, const void *base, size_t row_bytes, int rows, size_t step, int n,
+                      size_t frame_stride, int box_w_words, int box_h);
+
+// ---- host memory (hostmem.cu) ----------------------------------------------------------------
+// true when [p, p+bytes) lies inside memory this library pinned (rcv_pinned_alloc[_on]) or registered
+// (rcv_host_register / the "host.auto_register" cache): DMA-able without a bounce copy.
+bool host_range_pinned(const void *p, size_t bytes);
+// "host.auto_register": register [p, p+bytes) on first sight (LRU over a bounded set); false = leave pageable
+bool host_auto_register(const void *p, size_t bytes);
+void host_registry_shutdown();
+// rows x row_bytes strided copy on the pool's threads (the caller takes part); returns when done
+void host_copy2d(void *dst, size_t dstep, const void *src, size_t sstep, size_t row_bytes, int rows);
+// a band of a pageable destination: when `ev` (recorded after the band's D2H into the pinned bounce buffer) has
+// fired, the GPU's drain thread copies rows x row_bytes to the Mat and decrements *pending
+struct DrainJob {
+  cudaEvent_t ev;
+  void *dst;
+  size_t dstep;
+  const void *src;
+  size_t sstep, row_bytes;
+  int rows;
+  std::atomic<int> *pending, *failed;
+};
+void drain_submit(int device, const DrainJob &job);
+void drain_shutdown();
+int gpu_numa_node(int device);                 // -1 when unknown
+void bind_thread_to_gpu(int device);           // sched_setaffinity to the GPU's local_cpulist (if narrower)
+const char *last_error();
+
+// ---- multi-GPU workers (multi.cu) --------------------------------------------------------------
+// Runs fn on the worker thread of `device` (started on first use); rc and error text come back through *rc / err.
+struct MultiJoin;
+MultiJoin *multi_begin(int njobs);
+void multi_submit(MultiJoin *j, int device, int slot, int (*fn)(void *), void *arg);
+int multi_wait(MultiJoin *j);  // first failing rc (its message becomes this thread's last error); frees j
+void multi_shutdown();
+int devices_initialised(int *out, int cap);  // ordinals with a live context, ascending
 
 // ---- kernel launchers (device views only; enqueue on `s`) ------------------------
 int launch_cvt(Ctx *c, const DBatch &src, const DBatch &dst, int code, cudaStream_t s);

@@ -372,9 +372,9 @@ template <class Op, int S = kS, int NW = kNW>
 static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout, const char *band_opt,
                         cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr,
                         const float *ftaps = nullptr, int nftaps = 0) {
-  CUtensorMap tmap;
-  RCV_TRY(make_tmap_rows_u32(&tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
-                             kTileBytes / 4, kR));
+  const CUtensorMap *tmap = nullptr;  // cached per (base, geometry): the reference API calls once per frame on reused buffers
+  RCV_TRY(ctx_tmap_rows_u32(c, &tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
+                            kTileBytes / 4, kR));
   StripParams p = {};
   p.vec_store = 1;
   for (int k = 0; k < 3; ++k) {
@@ -428,7 +428,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     p.next_item = (unsigned long long *)ctr + which;
     p.reset_item = (unsigned long long *)ctr + (which ^ 1u);
   }
-  kern<<<grid, NW * 32, smem, s>>>(tmap, p);
+  kern<<<grid, NW * 32, smem, s>>>(*tmap, p);
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;

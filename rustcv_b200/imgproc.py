@@ -34,6 +34,11 @@ def init(device: int = 0) -> None:
     F.check(F.lib.rcv_init(device))
 
 
+def init_multi(ngpus: int = 0) -> None:
+    """GPUs 0..ngpus-1 (0 = every GPU of the box), one library worker thread per GPU."""
+    F.check(F.lib.rcv_init_multi(ngpus))
+
+
 def shutdown() -> None:
     F.check(F.lib.rcv_shutdown())
 
@@ -194,6 +199,100 @@ def yuyv_to_bgr_gaussian5_batch(srcs, dsts) -> None:
     da, m = _arr(dsts)
     assert n == m
     F.check(F.lib.rcv_yuyv_to_bgr_gaussian5_batch(sa, da, n))
+
+
+# ---- the same, sharded over several GPUs from ONE calling thread --------------
+def gaussian_blur_batch_multi(srcs, dsts, ngpus: int = 0, ksize=(5, 5), sigma_x: float = 0.0, sigma_y: float = 0.0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_gaussian_blur_batch_multi(sa, da, n, ngpus, ksize[0], ksize[1], sigma_x, sigma_y))
+
+
+def sobel_mag_batch_multi(srcs, mags, ngpus: int = 0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(mags)
+    assert n == m
+    F.check(F.lib.rcv_sobel_mag_batch_multi(sa, da, n, ngpus))
+
+
+def resize_batch_multi(srcs, dsts, ngpus: int = 0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_resize_bilinear_batch_multi(sa, da, n, ngpus))
+
+
+def warp_affine_batch_multi(srcs, dsts, M, ngpus: int = 0, inverse_map: bool = False, border_value: float = 0.0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    mm = (C.c_double * 6)(*[float(v) for v in np.asarray(M, dtype=np.float64).ravel()])
+    F.check(F.lib.rcv_warp_affine_batch_multi(sa, da, n, ngpus, mm, int(inverse_map), border_value))
+
+
+def cvt_color_batch_multi(srcs, dsts, code: int, ngpus: int = 0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_cvt_color_batch_multi(sa, da, n, ngpus, code))
+
+
+def yuyv_to_sobel_mag_batch_multi(srcs, mags, ngpus: int = 0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(mags)
+    assert n == m
+    F.check(F.lib.rcv_yuyv_to_sobel_mag_batch_multi(sa, da, n, ngpus))
+
+
+def yuyv_to_bgr_gaussian5_batch_multi(srcs, dsts, ngpus: int = 0) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    F.check(F.lib.rcv_yuyv_to_bgr_gaussian5_batch_multi(sa, da, n, ngpus))
+
+
+def _taps(k):
+    if k is None:
+        return None, 0
+    a = np.ascontiguousarray(k, dtype=np.int32)
+    return a, a.size
+
+
+def sep_filter2d_q8_batch(srcs, dsts, kx, ky) -> None:
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    ax, kw = _taps(kx)
+    ay, kh = _taps(ky)
+    ip = C.POINTER(C.c_int32)
+    F.check(F.lib.rcv_sep_filter2d_q8_batch(sa, da, n, ax.ctypes.data_as(ip), kw, ay.ctypes.data_as(ip), kh))
+
+
+def sep_filter2d_q8_batch_multi(srcs, dsts, ngpus: int = 0, kx=None, ky=None, kw: int = 0, kh: int = 0) -> None:
+    """kx = ky = None: every GPU filters with the kw + kh taps it received from set_kernel_broadcast."""
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    ip = C.POINTER(C.c_int32)
+    if kx is None:
+        F.check(F.lib.rcv_sep_filter2d_q8_batch_multi(sa, da, n, ngpus, None, kw, None, kh))
+        return
+    ax, kw = _taps(kx)
+    ay, kh = _taps(ky)
+    F.check(F.lib.rcv_sep_filter2d_q8_batch_multi(sa, da, n, ngpus, ax.ctypes.data_as(ip), kw, ay.ctypes.data_as(ip), kh))
+
+
+def set_kernel_broadcast(coeffs, root_device: int = 0, ngpus: int = 0) -> np.ndarray:
+    """The path's one collective: `coeffs` (f32) from GPU `root_device` to every GPU's coefficient
+    bank over NCCL.  Returns what each GPU received, (ngpus, count)."""
+    a = np.ascontiguousarray(coeffs, dtype=np.float32).ravel()
+    cnt = C.c_int()
+    F.check(F.lib.rcv_device_count(C.byref(cnt)))
+    got = np.zeros((max(cnt.value, 1), a.size), dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    F.check(F.lib.rcv_set_kernel_broadcast(a.ctypes.data_as(fp), a.size, root_device, ngpus, got.ctypes.data_as(fp)))
+    return got
 
 
 # ---- runtime knobs ---------------------------------------------------------------------------

@@ -23,7 +23,8 @@ def _elem(depth: int) -> int:
 
 
 class Mat:
-    __slots__ = ("data", "rows", "cols", "step", "channels", "depth", "loc", "device", "_c", "_pinned_ptr", "_owner")
+    __slots__ = ("data", "rows", "cols", "step", "channels", "depth", "loc", "device", "_pinned_ptr", "_owner",
+                 "_registered")
 
     def __init__(self):
         self.data = None  # np.uint8 1-D for host Mats, int (device pointer) for device Mats
@@ -34,9 +35,9 @@ class Mat:
         self.depth = U8
         self.loc = F.RCV_HOST
         self.device = 0
-        self._c = None
         self._pinned_ptr = None
         self._owner = None  # the batch allocation a device Mat was carved from
+        self._registered = None  # address page-locked in place by register()
 
     # -- constructors (mat.rs:18-40) ------------------------------------------------
     @staticmethod
@@ -78,14 +79,15 @@ class Mat:
         return m
 
     @staticmethod
-    def pinned(rows: int, cols: int, channels: int, depth: int = U8) -> "Mat":
-        """Host Mat in page-locked memory (rcv_pinned_alloc) for direct DMA."""
+    def pinned(rows: int, cols: int, channels: int, depth: int = U8, device: int = -1) -> "Mat":
+        """Host Mat in page-locked memory (rcv_pinned_alloc_on: on the NUMA node of GPU `device`
+        when the box has several) for direct DMA."""
         m = Mat()
         m.rows, m.cols, m.channels, m.depth = rows, cols, channels, depth
         m.step = cols * channels * _elem(depth)
         n = max(rows * m.step, 1)
         p = C.c_void_p()
-        F.check(F.lib.rcv_pinned_alloc(C.byref(p), n))
+        F.check(F.lib.rcv_pinned_alloc_on(device, C.byref(p), n))
         m._pinned_ptr = p.value
         m.data = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.value))[: rows * m.step]
         m.loc = F.RCV_HOST_PINNED
@@ -128,12 +130,32 @@ class Mat:
 
     def ensure_size(self, rows: int, cols: int, channels: int, depth: int = U8) -> None:
         """rustcv-camera/src/mat.rs:65-74 / videoio/mod.rs:192-199: (re)size a host dst the
-        way `read` does -- packed, reallocating only when the byte length changes."""
+        way `read` does -- packed, reallocating only when the byte length changes.  A buffer
+        that was page-locked in place is unregistered before it is dropped and the new one
+        registered again (what the Rust wrapper does)."""
         assert self.loc == F.RCV_HOST
         step = cols * channels * _elem(depth)
         if self.data is None or self.data.size != rows * step:
+            was_registered = self._registered is not None
+            self.unregister()
             self.data = np.zeros(rows * step, dtype=np.uint8)
+            if was_registered:
+                self.register()
         self.rows, self.cols, self.channels, self.depth, self.step = rows, cols, channels, depth, step
+
+    def register(self) -> "Mat":
+        """Page-locks this host Mat's buffer in place (rcv_host_register): the reference reuses
+        the Vec<u8> frame after frame, so one registration serves every later call."""
+        assert self.loc == F.RCV_HOST
+        if self._registered is None and self.data is not None and self.data.size:
+            F.check(F.lib.rcv_host_register(self.data.ctypes.data, self.data.size))
+            self._registered = self.data.ctypes.data
+        return self
+
+    def unregister(self) -> None:
+        if self._registered is not None:
+            p, self._registered = self._registered, None
+            F.check(F.lib.rcv_host_unregister(p))
 
     # -- conversions ----------------------------------------------------------------------
     def to_numpy(self) -> np.ndarray:
@@ -177,11 +199,14 @@ class Mat:
             c.data = self.data.ctypes.data if self.data is not None and self.data.size else None
         c.rows, c.cols, c.step = self.rows, self.cols, self.step
         c.channels, c.depth, c.loc, c.device = self.channels, self.depth, self.loc, self.device
-        c._keep = self  # the POD borrows self.data: keep the owner alive as long as the POD
-        self._c = c
+        # the POD borrows self.data: it keeps the owner alive, never the other way round (a Mat holding its own
+        # POD would be a reference cycle, and device / pinned storage would wait for the cyclic GC)
+        c._keep = self
         return c
 
     def free(self) -> None:
+        if self._registered is not None:
+            self.unregister()
         if self.loc == F.RCV_DEVICE and self.data and self._owner is None:
             c = self.c()
             F.check(F.lib.rcv_mat_free_device(C.byref(c)))
