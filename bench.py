@@ -635,6 +635,33 @@ def main() -> None:
         sustained = {"steps": n_sus, "seconds": n_sus * sus_ms * 1e-3, "ms_per_step": sus_ms,
                      "value": total_pix / (sus_ms * 1e-3) / 1e6, "achieved": ach, "frac": ach / peak,
                      "clocks": sampler.window(t0 + 0.2, t1) if rank == 0 else None}
+        # context for that number: what a PLAIN COPY (the kernel MEASURED_PEAKS.json's hbm_gbs was taken with, torch
+        # copy_, as a burst) sustains over the same length of time on this GPU, right after -- same power cap, same clocks
+        if rank == 0:
+            a = torch.empty(F_ * PIX * CN, dtype=torch.uint8, device=dev)
+            b = torch.empty_like(a)
+            for _ in range(3):
+                b.copy_(a)
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            b.copy_(a)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            n_cp = max(10, int(args.sustained_s * 1e3 / max(c0.elapsed_time(c1), 1e-3)))
+            tc0 = time.time()
+            c0.record()
+            for _ in range(n_cp):
+                b.copy_(a)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            tc1 = time.time()
+            cp_gbs = 2 * a.numel() * n_cp / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            sustained["plain_copy_sustained"] = {"gbs": cp_gbs, "seconds": c0.elapsed_time(c1) * 1e-3,
+                                                 "frac_of_this": ach / cp_gbs, "clocks": sampler.window(tc0 + 0.2, tc1),
+                                                 "what": "torch b.copy_(a) over the same 2 x 796 MB, looped for the same time"}
+            del a, b
+        barrier()
 
     # ---- single synchronous call on a device-resident Mat (the reference API's own shape) --------------
     calls = {}

@@ -16,6 +16,7 @@ pub const RCV_ERR_CUDA: c_int = -4;
 pub const RCV_ERR_UNSUPPORTED: c_int = -5;
 pub const RCV_ERR_NOT_INIT: c_int = -6;
 pub const RCV_ERR_NOMEM: c_int = -7;
+pub const RCV_ERR_NCCL: c_int = -8;
 
 pub const RCV_U8: u8 = 0;
 pub const RCV_F32: u8 = 1;
@@ -49,6 +50,7 @@ pub struct RcvMat {
 #[link(name = "rcv_imgproc", kind = "dylib")]
 extern "C" {
     pub fn rcv_init(device: c_int) -> c_int;
+    pub fn rcv_init_multi(ngpus: i32) -> c_int;
     pub fn rcv_shutdown() -> c_int;
     pub fn rcv_last_error() -> *const c_char;
     pub fn rcv_sync(device: c_int) -> c_int;
@@ -58,7 +60,10 @@ extern "C" {
     pub fn rcv_mat_upload(host: *const RcvMat, dev: *mut RcvMat) -> c_int;
     pub fn rcv_mat_download(dev: *const RcvMat, host: *mut RcvMat) -> c_int;
     pub fn rcv_pinned_alloc(ptr: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn rcv_pinned_alloc_on(device: i32, ptr: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn rcv_pinned_free(ptr: *mut c_void) -> c_int;
+    pub fn rcv_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn rcv_host_unregister(ptr: *mut c_void) -> c_int;
 
     pub fn rcv_cvt_color(src: *const RcvMat, dst: *mut RcvMat, code: i32) -> c_int;
     pub fn rcv_yuyv_to_bgr(src: *const RcvMat, dst: *mut RcvMat) -> c_int;
@@ -90,4 +95,16 @@ extern "C" {
     pub fn rcv_warp_affine_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, m: *const f64, inverse_map: i32, border_value: f64) -> c_int;
     pub fn rcv_sobel_mag_batch(srcs: *const RcvMat, mags: *mut RcvMat, n: i32) -> c_int;
     pub fn rcv_cvt_color_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, code: i32) -> c_int;
+    pub fn rcv_sep_filter2d_q8_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, kx: *const i32, kw: i32, ky: *const i32, kh: i32) -> c_int;
+
+    // the same batches sharded over several GPUs from the ONE calling thread (frame j -> GPU j mod ngpus)
+    pub fn rcv_gaussian_blur_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, kw: i32, kh: i32, sigma_x: f64, sigma_y: f64) -> c_int;
+    pub fn rcv_sobel_mag_batch_multi(srcs: *const RcvMat, mags: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
+    pub fn rcv_resize_bilinear_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
+    pub fn rcv_warp_affine_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, m: *const f64, inverse_map: i32, border_value: f64) -> c_int;
+    pub fn rcv_cvt_color_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, code: i32) -> c_int;
+    pub fn rcv_yuyv_to_sobel_mag_batch_multi(srcs_yuyv: *const RcvMat, mags_f32: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
+    pub fn rcv_yuyv_to_bgr_gaussian5_batch_multi(srcs_yuyv: *const RcvMat, dsts_bgr: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
+    pub fn rcv_sep_filter2d_q8_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, kx: *const i32, kw: i32, ky: *const i32, kh: i32) -> c_int;
+    pub fn rcv_set_kernel_broadcast(coeffs: *const f32, count: i32, root_device: i32, ngpus: i32, received: *mut f32) -> c_int;
 }

@@ -1360,14 +1360,18 @@ def test_yuyv_to_bgr_gaussian5_chain_batch_bands(rcv, oracle):
         assert_same(d.to_numpy(), want, "forced two-kernel chain")
     finally:
         R.imgproc.set_option("yuyvgauss.force_chain", 0)
-    for shape in ((5, 6), (7, 30), (12, 33)):
+    for shape in ((5, 6), (7, 30), (12, 34)):
         y2 = oracle.fill_u8(79, shape[0] * shape[1] * 2).reshape(shape[0], shape[1], 2)
         d = R.Mat.empty()
         R.imgproc.yuyv_to_bgr_gaussian5(R.Mat.from_numpy(y2), d)
-        got, ref = d.to_numpy(), _yuyv_gauss_oracle(oracle, y2)
-        if shape[1] & 1:  # the conversion leaves the odd last pixel untouched (videoio/mod.rs:350): compare the rest
-            got, ref = got[:, :shape[1] - 3], ref[:, :shape[1] - 3]
-        assert_same(got, ref, f"small {shape}")
+        assert_same(d.to_numpy(), _yuyv_gauss_oracle(oracle, y2), f"small {shape}")
+    # an odd width would leave the BGR intermediate's last column unconverted (videoio/mod.rs:350) for the blur to
+    # read: rejected, like rcv_yuyv_to_sobel_mag
+    from rustcv_b200 import _ffi as F
+    y3 = oracle.fill_u8(79, 12 * 33 * 2).reshape(12, 33, 2)
+    with pytest.raises(F.RcvError) as e:
+        R.imgproc.yuyv_to_bgr_gaussian5(R.Mat.from_numpy(y3), R.Mat.empty())
+    assert e.value.code == F.RCV_ERR_SIZE
     n, hh, ww = 4, 96, 720
     frames = [oracle.fill_u8(800 + j, hh * ww * 2).reshape(hh, ww, 2) for j in range(n)]
     src = R.Mat.device_batch(n, hh, ww, 2)
