@@ -48,41 +48,117 @@ struct SepArgs {
   typename SepTraits<T>::Tap kx[kMaxTaps + 1], ky[kMaxTaps + 1];
 };
 
-constexpr int kSepTBX = 128, kSepTBY = 32, kSepThreads = 256;
-constexpr int kSepMaxRW = kSepTBX + (kMaxTaps - 1) * 4;  // widest raw tile row (elements)
+// ---------------------------------------------------------------------------------------
+// register-tiled tap chains
+// ---------------------------------------------------------------------------------------
+// acc[m] (m < N) <- mac(k[j], v(m + j), acc[m]) for j = 0 .. kn-1 in ASCENDING j (the oracle's fmaf order), where
+// v(i) = load(i), i = 0 .. kn + N - 2.  Every v(i) and every tap is loaded ONCE and used for up to N outputs, so
+// the loop runs at ~(1 + 2/N) instructions per multiply-add instead of the 3 of a one-output-per-thread loop
+// (load value, load tap, fma) -- the old general-case kernels were shared-memory-instruction bound at 3-5 % of the
+// HBM roofline.  The last N taps live in a register ring indexed by compile-time slots (tap j in slot j % N).
+// KN > 0: the tap count is a compile-time constant (everything unrolls, no predicates); KN == 0: run time.
+template <int N, int KN, class Acc, class Tap, class Load, class Mac>
+__device__ __forceinline__ void tap_chain(Acc (&acc)[N], const Tap *__restrict__ k, int kn_rt, Load load, Mac mac) {
+  const int kn = KN > 0 ? KN : kn_rt;
+  Tap kk[N];
+#pragma unroll
+  for (int m = 0; m < N; ++m) kk[m] = Tap(0);
+  if constexpr (KN > 0) {
+#pragma unroll
+    for (int i = 0; i < KN + N - 1; ++i) {
+      const Acc v = load(i);
+      if (i < KN) kk[i % N] = k[i];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const int j = i - m;
+        if (j >= 0 && j < KN) acc[m] = mac(kk[(j + N) % N], v, acc[m]);
+      }
+    }
+  } else {
+  // ramp-up: i = 0 .. N-2, outputs m <= i
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) {
+    if (i < kn + N - 1) {
+      const Acc v = load(i);
+      if (i < kn) kk[i % N] = k[i];
+#pragma unroll
+      for (int m = 0; m <= i; ++m)
+        if (i - m < kn) acc[m] = mac(kk[(i - m) % N], v, acc[m]);
+    }
+  }
+  // steady state: N values per trip, every output takes every value (i0 = N-1 mod N throughout)
+  int i0 = N - 1;
+  for (; i0 + N - 1 <= kn - 1; i0 += N) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      const Acc v = load(i0 + u);
+      kk[(N - 1 + u) % N] = k[i0 + u];
+#pragma unroll
+      for (int m = 0; m < N; ++m) acc[m] = mac(kk[(2 * N - 1 + u - m) % N], v, acc[m]);
+    }
+  }
+  // ramp-down: the remaining i0 .. kn + N - 2 (at most 2N - 2 values)
+#pragma unroll
+  for (int u = 0; u < 2 * N - 2; ++u) {
+    const int i = i0 + u;
+    if (i < kn + N - 1) {
+      const Acc v = load(i);
+      if (i < kn) kk[(N - 1 + u) % N] = k[i];
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+        if (i - m < kn) acc[m] = mac(kk[(4 * N - 1 + u - m) % N], v, acc[m]);
+    }
+  }
+  }
+}
 
-// Warp w works on tile rows w, w+8, ...; lane l on element columns l, l+32, ... : no divisions in
-// the loops (the reflected source offset of every raw-tile column is computed once per thread),
-// conflict-free shared-memory rows, coalesced global rows.
-template <typename T>
-__global__ void __launch_bounds__(kSepThreads) k_sepfilter(const SepArgs<T> a) {
+// lanes of a warp that work on a tile row: a lane owns one channel of a block of N pixels, so only whole pixels
+constexpr int tile_lanes(int cn) { return 32 / cn * cn; }
+
+constexpr int kSepTBY = 32, kSepThreads = 256, kSepN = 8;  // tile rows; outputs per thread per pass
+constexpr int kSepMaxTBX = 32 * kSepN;                     // tile width in element columns (240 for 3 channels)
+constexpr int kSepMaxRW = kSepMaxTBX + (kMaxTaps - 1) * 4;  // widest raw tile row (elements)
+
+// Stage 2 (horizontal): warp w takes tile rows w, w+8, ...; a lane computes the kSepN outputs of ONE channel of a
+// block of kSepN pixels (element columns x0 + m*cn) from the kw + kSepN - 1 raw values x0 + i*cn.
+// Stage 3 (vertical): a thread computes kSepN consecutive rows of one element column from kh + kSepN - 1 values of
+// the horizontally filtered tile.
+template <typename T, int KN>
+__global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant__ SepArgs<T> a) {
   typedef typename SepTraits<T>::Acc Acc;
+  typedef typename SepTraits<T>::Tap Tap;
   extern __shared__ __align__(16) uint8_t smem[];
-  const int rx = a.kw / 2, ry = a.kh / 2;
-  const int RW = kSepTBX + (a.kw - 1) * a.cn;  // raw tile width (elements)
-  const int RH = kSepTBY + a.kh - 1;           // raw tile height
+  const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
+  const int rx = kw / 2, ry = kh / 2;
+  const int lanes = 32 / a.cn * a.cn;
+  const int TBX = lanes * kSepN;           // tile width (element columns)
+  const int RW = TBX + (kw - 1) * a.cn;    // raw tile width (elements)
+  const int RH = kSepTBY + kh - 1;         // raw tile height
   T *raw = (T *)smem;
   Acc *mid = (Acc *)(smem + (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NWARP = kSepThreads / 32;
 
   const int ncols = a.cols * a.cn;
-  const int ex0 = blockIdx.x * kSepTBX;  // first element column of the tile
+  const int ex0 = blockIdx.x * TBX;  // first element column of the tile
   const int y0 = blockIdx.y * kSepTBY;
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
 
-  // source element offset of raw-tile column lane + 32*i (REFLECT_101 on the pixel index)
+  // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][reflect column of x]; the reflected source offset of every
+  // raw-tile column is computed once per thread (no divisions in the row loop)
   constexpr int NX = (kSepMaxRW + 31) / 32;
   int xoff[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
     const int x = lane + 32 * i;
-    const int ex = ex0 + x - rx * a.cn;
-    const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);  // floor division
-    xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+    xoff[i] = 0;
+    if (x < RW) {
+      const int ex = ex0 + x - rx * a.cn;
+      const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);  // floor division
+      xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+    }
   }
-  // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][xoff(x)]
   for (int r = warp; r < RH; r += NWARP) {
     const T *srow = (const T *)(src + (size_t)reflect101(y0 + r - ry, a.rows) * a.sstep);
     T *rrow = raw + r * RW;
@@ -94,44 +170,76 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const SepArgs<T> a) {
   }
   __syncthreads();
   // stage 2: horizontal
-  for (int r = warp; r < RH; r += NWARP) {
+  if (lane < lanes) {
+    const int x0 = lane / a.cn * (kSepN * a.cn) + lane % a.cn;
+    for (int r = warp; r < RH; r += NWARP) {
+      const T *p = raw + r * RW + x0;
+      Acc acc[kSepN];
 #pragma unroll
-    for (int i = 0; i < kSepTBX / 32; ++i) {
-      const int x = lane + 32 * i;
-      const T *p = raw + r * RW + x;
-      Acc acc = 0;
-      for (int j = 0; j < a.kw; ++j) {
-        if (sizeof(T) == 1)
-          acc += (Acc)a.kx[j] * (Acc)p[j * a.cn];
-        else
-          acc = fmaf((float)a.kx[j], (float)p[j * a.cn], (float)acc);
-      }
-      mid[r * kSepTBX + x] = acc;
+      for (int m = 0; m < kSepN; ++m) acc[m] = 0;
+      const int cn = a.cn;
+      if (sizeof(T) == 1)
+        tap_chain<kSepN, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
+                             [](Tap k, Acc v, Acc c) { return (Acc)(c + (Acc)k * v); });
+      else
+        tap_chain<kSepN, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
+                             [](Tap k, Acc v, Acc c) { return (Acc)fmaf((float)k, (float)v, (float)c); });
+      Acc *o = mid + r * TBX + x0;
+#pragma unroll
+      for (int m = 0; m < kSepN; ++m) o[m * cn] = acc[m];
     }
   }
   __syncthreads();
-  // stage 3: vertical
-  for (int r = warp; r < kSepTBY; r += NWARP) {
-    const int y = y0 + r;
-    if (y >= a.rows) break;
+  // stage 3: vertical -- thread t: element column t % TBX (+ multiples of the thread count), row group
+  for (int task = threadIdx.x; task < TBX * (kSepTBY / kSepN); task += kSepThreads) {
+    const int x = task % TBX, r0 = task / TBX * kSepN;
+    const int ex = ex0 + x;
+    if (ex >= ncols || y0 + r0 >= a.rows) continue;
+    const Acc *p = mid + r0 * TBX + x;
+    Acc acc[kSepN];
 #pragma unroll
-    for (int i = 0; i < kSepTBX / 32; ++i) {
-      const int x = lane + 32 * i;
-      const int ex = ex0 + x;
-      if (ex >= ncols) continue;
-      const Acc *p = mid + r * kSepTBX + x;
+    for (int m = 0; m < kSepN; ++m) acc[m] = sizeof(T) == 1 ? (Acc)32768u : (Acc)0;
+    if (sizeof(T) == 1)
+      tap_chain<kSepN, KN>(acc, (const Tap *)a.ky, kh, [&](int i) { return p[i * TBX]; },
+                           [](Tap k, Acc v, Acc c) { return (Acc)(c + (Acc)k * v); });
+    else
+      tap_chain<kSepN, KN>(acc, (const Tap *)a.ky, kh, [&](int i) { return p[i * TBX]; },
+                           [](Tap k, Acc v, Acc c) { return (Acc)fmaf((float)k, (float)v, (float)c); });
+#pragma unroll
+    for (int m = 0; m < kSepN; ++m) {
+      const int y = y0 + r0 + m;
+      if (y >= a.rows) break;
       if (sizeof(T) == 1) {
-        uint32_t acc = 32768u;
-        for (int k = 0; k < a.kh; ++k) acc += (uint32_t)a.ky[k] * (uint32_t)p[k * kSepTBX];
-        acc >>= 16;
-        ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)(acc > 255u ? 255u : acc);
+        const uint32_t v = (uint32_t)acc[m] >> 16;
+        ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)(v > 255u ? 255u : v);
       } else {
-        float acc = 0.0f;
-        for (int k = 0; k < a.kh; ++k) acc = fmaf((float)a.ky[k], (float)p[k * kSepTBX], acc);
-        ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+        ((float *)(dst + (size_t)y * a.dstep))[ex] = (float)acc[m];
       }
     }
   }
+}
+
+template <typename T, int KN>
+static int launch_sep_kn(const SepArgs<T> &a, int n, cudaStream_t s) {
+  const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
+  const int TBX = tile_lanes(a.cn) * kSepN;
+  const int RW = TBX + (kw - 1) * a.cn, RH = kSepTBY + kh - 1;
+  const size_t smem = (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15) + (size_t)TBX * RH * 4;
+  auto kern = k_sepfilter<T, KN>;
+  static size_t attr_smem[16] = {};  // per instantiation, per device: the largest size set so far
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_smem[dev & 15] < smem) {
+    RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev & 15] = smem;
+  }
+  const int ncols = a.cols * a.cn;
+  dim3 grid(ceil_div(ncols, TBX), ceil_div(a.rows, kSepTBY), n);
+  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  kern<<<grid, kSepThreads, smem, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
 }
 
 template <typename T>
@@ -154,17 +262,19 @@ static int launch_sep(const DBatch &src, const DBatch &dst, const typename SepTr
   a.kh = kh;
   for (int i = 0; i < kw; ++i) a.kx[i] = kx[i];
   for (int i = 0; i < kh; ++i) a.ky[i] = ky[i];
-  const int RW = kSepTBX + (kw - 1) * a.cn, RH = kSepTBY + kh - 1;
-  size_t smem = (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15) + (size_t)kSepTBX * RH * 4;
-  auto kern = k_sepfilter<T>;
-  RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ncols = a.cols * a.cn;
-  dim3 grid(ceil_div(ncols, kSepTBX), ceil_div(a.rows, kSepTBY), src.n);
-  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
-  kern<<<grid, kSepThreads, smem, s>>>(a);
-  count_launch();
-  RCV_CUDA(cudaGetLastError());
-  return RCV_OK;
+  // square kernels of the common sizes: compile-time tap counts (fully unrolled chains, no predicates)
+  if (kw == kh) {
+    switch (kw) {
+      case 3: return launch_sep_kn<T, 3>(a, src.n, s);
+      case 5: return launch_sep_kn<T, 5>(a, src.n, s);
+      case 7: return launch_sep_kn<T, 7>(a, src.n, s);
+      case 9: return launch_sep_kn<T, 9>(a, src.n, s);
+      case 11: return launch_sep_kn<T, 11>(a, src.n, s);
+      case 13: return launch_sep_kn<T, 13>(a, src.n, s);
+      case 15: return launch_sep_kn<T, 15>(a, src.n, s);
+    }
+  }
+  return launch_sep_kn<T, 0>(a, src.n, s);
 }
 
 int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s);
@@ -364,65 +474,107 @@ struct F2dArgs {
   float delta;
 };
 
-constexpr int kF2dTBX = 64, kF2dTBY = 16, kF2dThreads = 256;
-constexpr int kF2dMaxRW = kF2dTBX + (kMaxTaps - 1) * 4;
+constexpr int kF2dTBY = 32, kF2dThreads = 256, kF2dN = 8;
+constexpr int kF2dMaxRW = 32 * kF2dN + (kMaxTaps - 1) * 4;
 
-template <typename T>
+// A lane computes the kF2dN outputs of one channel of a block of kF2dN pixels of one tile row: kernel row by kernel
+// row (ascending), each a tap_chain over that source row -- per output exactly the oracle's row-major fmaf chain.
+template <typename T, int KN>
 __global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int rx = a.kw / 2, ry = a.kh / 2;
-  const int RW = kF2dTBX + (a.kw - 1) * a.cn;
-  const int RH = kF2dTBY + a.kh - 1;
+  const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
+  const int rx = kw / 2, ry = kh / 2;
+  const int lanes = 32 / a.cn * a.cn;
+  const int TBX = lanes * kF2dN;
+  const int RW = TBX + (kw - 1) * a.cn;
+  const int RH = kF2dTBY + kh - 1;
   float *taps = (float *)smem;
-  T *raw = (T *)(smem + (((size_t)a.kw * a.kh * 4 + 15) & ~(size_t)15));
+  float *raw = (float *)(smem + (((size_t)kw * kh * 4 + 15) & ~(size_t)15));  // staged as f32: converted once, not per tap
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NWARP = kF2dThreads / 32;
   const int ncols = a.cols * a.cn;
-  const int ex0 = blockIdx.x * kF2dTBX, y0 = blockIdx.y * kF2dTBY;
+  const int ex0 = blockIdx.x * TBX, y0 = blockIdx.y * kF2dTBY;
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
-  for (int i = threadIdx.x; i < a.kw * a.kh; i += kF2dThreads) taps[i] = a.taps[i];
+  for (int i = threadIdx.x; i < kw * kh; i += kF2dThreads) taps[i] = a.taps[i];
   constexpr int NX = (kF2dMaxRW + 31) / 32;
   int xoff[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
     const int x = lane + 32 * i;
-    const int ex = ex0 + x - rx * a.cn;
-    const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
-    xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+    xoff[i] = 0;
+    if (x < RW) {
+      const int ex = ex0 + x - rx * a.cn;
+      const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
+      xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+    }
   }
   for (int r = warp; r < RH; r += NWARP) {
     const T *srow = (const T *)(src + (size_t)reflect101(y0 + r - ry, a.rows) * a.sstep);
-    T *rrow = raw + r * RW;
+    float *rrow = raw + r * RW;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const int x = lane + 32 * i;
-      if (x < RW) rrow[x] = srow[xoff[i]];
+      if (x < RW) rrow[x] = (float)srow[xoff[i]];
     }
   }
   __syncthreads();
+  if (lane >= lanes) return;
+  const int cn = a.cn;
+  const int x0 = lane / cn * (kF2dN * cn) + lane % cn;
   for (int r = warp; r < kF2dTBY; r += NWARP) {
     const int y = y0 + r;
     if (y >= a.rows) break;
+    float acc[kF2dN];
 #pragma unroll
-    for (int i = 0; i < kF2dTBX / 32; ++i) {
-      const int x = lane + 32 * i;
-      const int ex = ex0 + x;
+    for (int m = 0; m < kF2dN; ++m) acc[m] = a.delta;
+    for (int ki = 0; ki < kh; ++ki) {
+      const float *p = raw + (r + ki) * RW + x0;
+      tap_chain<kF2dN, KN>(acc, (const float *)(taps + ki * kw), kw, [&](int i) { return p[i * cn]; },
+                           [](float k, float v, float c) { return fmaf(k, v, c); });
+    }
+#pragma unroll
+    for (int m = 0; m < kF2dN; ++m) {
+      const int ex = ex0 + x0 + m * cn;
       if (ex >= ncols) continue;
-      float acc = a.delta;
-      for (int ki = 0; ki < a.kh; ++ki) {
-        const T *p = raw + (r + ki) * RW + x;
-        const float *t = taps + ki * a.kw;
-        for (int kj = 0; kj < a.kw; ++kj) acc = fmaf(t[kj], (float)p[kj * a.cn], acc);
-      }
       if (sizeof(T) == 1) {
-        int v = __float2int_rn(acc);  // round half to even, saturating conversion
+        int v = __float2int_rn(acc[m]);  // round half to even, saturating conversion
         ((uint8_t *)(dst + (size_t)y * a.dstep))[ex] = (uint8_t)min(max(v, 0), 255);
       } else {
-        ((float *)(dst + (size_t)y * a.dstep))[ex] = acc;
+        ((float *)(dst + (size_t)y * a.dstep))[ex] = acc[m];
       }
     }
   }
+}
+
+template <typename T, int KN>
+static int launch_f2d_kn(const F2dArgs &a, int n, cudaStream_t s) {
+  const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
+  const int TBX = tile_lanes(a.cn) * kF2dN;
+  const int RW = TBX + (kw - 1) * a.cn, RH = kF2dTBY + kh - 1;
+  const size_t smem = (((size_t)kw * kh * 4 + 15) & ~(size_t)15) + (size_t)RW * RH * sizeof(float);
+  auto kern = k_filter2d<T, KN>;
+  static size_t attr_smem[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_smem[dev & 15] < smem) {
+    RCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev & 15] = smem;
+  }
+  dim3 grid(ceil_div(a.cols * a.cn, TBX), ceil_div(a.rows, kF2dTBY), n);
+  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
+  kern<<<grid, kF2dThreads, smem, s>>>(a);
+  count_launch();
+  RCV_CUDA(cudaGetLastError());
+  return RCV_OK;
+}
+
+template <typename T>
+static int launch_f2d_t(const F2dArgs &a, int n, cudaStream_t s) {
+  if (a.kw == a.kh && a.kw == 3) return launch_f2d_kn<T, 3>(a, n, s);
+  if (a.kw == a.kh && a.kw == 5) return launch_f2d_kn<T, 5>(a, n, s);
+  if (a.kw == a.kh && a.kw == 7) return launch_f2d_kn<T, 7>(a, n, s);
+  return launch_f2d_kn<T, 0>(a, n, s);
 }
 
 int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
@@ -441,21 +593,7 @@ int launch_filter2d(Ctx *c, const DBatch &src, const DBatch &dst, const float *k
   RCV_CUDA(cudaMemcpyAsync(dtaps, k, (size_t)kw * kh * sizeof(float), cudaMemcpyHostToDevice, s));
   F2dArgs a{src.v.data, src.v.step, src.frame_stride, dst.v.data, dst.v.step, dst.frame_stride, src.v.rows,
             src.v.cols, src.v.cn, kw, kh, (const float *)dtaps, delta};
-  const size_t es = src.v.elem();
-  const int RW = kF2dTBX + (kw - 1) * a.cn, RH = kF2dTBY + kh - 1;
-  size_t smem = (((size_t)kw * kh * 4 + 15) & ~(size_t)15) + (size_t)RW * RH * es;
-  dim3 grid(ceil_div(a.cols * a.cn, kF2dTBX), ceil_div(a.rows, kF2dTBY), src.n);
-  if (grid.y > 65535 || grid.z > 65535) return fail(RCV_ERR_UNSUPPORTED, "image too tall / batch too large");
-  if (src.v.depth == RCV_U8) {
-    RCV_CUDA(cudaFuncSetAttribute(k_filter2d<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_filter2d<uint8_t><<<grid, kF2dThreads, smem, s>>>(a);
-  } else {
-    RCV_CUDA(cudaFuncSetAttribute(k_filter2d<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_filter2d<float><<<grid, kF2dThreads, smem, s>>>(a);
-  }
-  count_launch();
-  RCV_CUDA(cudaGetLastError());
-  return RCV_OK;
+  return src.v.depth == RCV_U8 ? launch_f2d_t<uint8_t>(a, src.n, s) : launch_f2d_t<float>(a, src.n, s);
 }
 
 // ---------------------------------------------------------------------------------------

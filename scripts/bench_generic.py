@@ -57,16 +57,33 @@ def case(name):
 
 
 if case("gauss"):
-    for ks, sg in (((3, 3), 0.0), ((7, 7), 1.5), ((5, 5), 1.0), ((11, 11), 0.0)):
+    for ks, sg in (((3, 3), 0.0), ((7, 7), 1.5), ((5, 5), 1.0), ((9, 9), 1.5), ((11, 11), 0.0), ((13, 13), 2.0), ((15, 15), 0.0),
+                   ((31, 31), 5.0)):
         report(f"gauss u8c3 4K {ks} s{sg}", timeit(lambda: I.gaussian_blur(bgr, out3, ks, sg)), 6 * H * W)
     f = dev(O.fill_f32(3, 1080 * 1920).reshape(1080, 1920))
     fo = f.like()
     report("gauss f32c1 1080p 5x5 s1.1", timeit(lambda: I.gaussian_blur(f, fo, (5, 5), 1.1)), 8 * 1080 * 1920)
+    report("gauss f32c1 1080p 11x11 s2", timeit(lambda: I.gaussian_blur(f, fo, (11, 11), 2.0)), 8 * 1080 * 1920)
+    f3 = dev(O.fill_f32(3, 1080 * 1920 * 3).reshape(1080, 1920, 3))
+    fo3 = f3.like()
+    report("gauss f32c3 1080p 5x5 s1.1", timeit(lambda: I.gaussian_blur(f3, fo3, (5, 5), 1.1)), 24 * 1080 * 1920)
+    report("gauss f32c3 1080p 11x11 s2", timeit(lambda: I.gaussian_blur(f3, fo3, (11, 11), 2.0)), 24 * 1080 * 1920)
+if case("gauss11"):
+    report("gauss u8c3 4K (11, 11) s0.0", timeit(lambda: I.gaussian_blur(bgr, out3, (11, 11), 0.0)), 6 * H * W)
+if case("f2d5"):
+    k5 = np.ones((5, 5), np.float32) / 25
+    report("filter2d u8c3 4K 5x5", timeit(lambda: I.filter2d(bgr, out3, k5)), 6 * H * W)
 if case("filter2d"):
     k = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
     report("filter2d u8c3 4K 3x3", timeit(lambda: I.filter2d(bgr, out3, k)), 6 * H * W)
     k5 = np.ones((5, 5), np.float32) / 25
     report("filter2d u8c3 4K 5x5", timeit(lambda: I.filter2d(bgr, out3, k5)), 6 * H * W)
+    k7 = np.ones((7, 7), np.float32) / 49
+    report("filter2d u8c3 4K 7x7", timeit(lambda: I.filter2d(bgr, out3, k7)), 6 * H * W)
+    ff = dev(O.fill_f32(3, 1080 * 1920 * 3).reshape(1080, 1920, 3))
+    ffo = ff.like()
+    report("filter2d f32c3 1080p 3x3", timeit(lambda: I.filter2d(ff, ffo, k)), 24 * 1080 * 1920)
+    report("filter2d f32c3 1080p 5x5", timeit(lambda: I.filter2d(ff, ffo, k5)), 24 * 1080 * 1920)
 if case("cvt"):
     g = bgr.like(channels=1)
     report("bgr2gray 4K", timeit(lambda: I.cvt_color(bgr, g, I.COLOR_BGR2GRAY)), 4 * H * W)

@@ -1,0 +1,106 @@
+"""GPU suite, part 3: the general-case (register-tiled) separable / dense filter kernels of filter.cu -- every tap
+count (compile-time 3 / 5 / 7 and run-time chains incl. 1, even sizes, 9..31, non-square), every channel count,
+u8 and f32, images that span several CTA tiles with ragged edges, batches.  Bit-exact against the oracle (f32:
+the oracle's fmaf order, 0 ULP)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FORCE = ("gauss.force_generic", "sepf32.force_generic", "f2d.force_generic")
+
+
+@pytest.fixture()
+def generic(rcv):
+    for o in FORCE:
+        rcv.imgproc.set_option(o, 1)
+    yield rcv
+    for o in FORCE:
+        rcv.imgproc.set_option(o, 0)
+
+
+def _img(oracle, seed, h, w, cn, f32):
+    shape = (h, w) if cn == 1 else (h, w, cn)
+    if f32:
+        return oracle.fill_f32(seed, h * w * cn).reshape(shape)
+    return oracle.fill_u8(seed, h * w * cn).reshape(shape)
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("kw,kh", [(1, 1), (2, 2), (3, 3), (5, 5), (7, 7), (9, 9), (11, 11), (15, 15), (31, 31), (9, 3), (3, 13),
+                                   (8, 5), (16, 17)])
+def test_separable_u8_q8_general_kernel(generic, oracle, cn, kw, kh):
+    R = generic
+    rng = np.random.default_rng(kw * 100 + kh)
+    h, w = 75, 301  # 3 tile rows of 32; 301*cn element columns: 2..5 tiles of 240/256 with a ragged last one
+    a = _img(oracle, 2000 + cn, h, w, cn, False)
+    kx = rng.integers(-40, 90, size=kw).astype(np.int32)
+    ky = rng.integers(-40, 90, size=kh).astype(np.int32)
+    s = R.Mat.from_numpy(a).upload()
+    d = s.like()
+    R.imgproc.sep_filter2d(s, d, kx, ky)
+    assert (d.to_numpy() == oracle.sepfilter_u8_q8(a, kx, ky)).all(), f"cn{cn} {kw}x{kh}"
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("kw,kh", [(1, 1), (3, 3), (5, 5), (7, 7), (9, 9), (13, 13), (31, 31), (5, 11), (12, 4)])
+def test_separable_f32_general_kernel(generic, oracle, cn, kw, kh):
+    R = generic
+    rng = np.random.default_rng(kw * 100 + kh + 7)
+    h, w = 70, 203
+    a = _img(oracle, 2100 + cn, h, w, cn, True)
+    kx = rng.normal(size=kw).astype(np.float32)
+    ky = rng.normal(size=kh).astype(np.float32)
+    s = R.Mat.from_numpy(a).upload()
+    d = s.like()
+    R.imgproc.sep_filter2d(s, d, kx, ky)
+    want = oracle.sepfilter_f32(a, kx, ky)
+    assert (d.to_numpy().view(np.int32) == want.view(np.int32)).all(), f"cn{cn} {kw}x{kh}"
+
+
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("kw,kh", [(1, 1), (3, 3), (5, 5), (7, 7), (9, 9), (4, 4), (7, 3), (3, 11), (15, 15)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_dense_filter2d_general_kernel(generic, oracle, cn, kw, kh, f32):
+    R = generic
+    rng = np.random.default_rng(kw * 31 + kh)
+    h, w = 53, 270  # 4 tile rows of 16; ragged tiles
+    a = _img(oracle, 2200 + cn, h, w, cn, f32)
+    k = rng.normal(size=(kh, kw)).astype(np.float32)
+    if not f32:
+        k = (k / max(1e-3, np.abs(k).sum()) * 1.7).astype(np.float32)  # some saturation, both ways
+    s = R.Mat.from_numpy(a).upload()
+    d = s.like()
+    R.imgproc.filter2d(s, d, k, delta=0.375)
+    want = oracle.filter2d(a, k, 0.375)
+    if f32:
+        assert (d.to_numpy().view(np.int32) == want.view(np.int32)).all(), f"cn{cn} {kw}x{kh}"
+    else:
+        assert (d.to_numpy() == want).all(), f"cn{cn} {kw}x{kh}"
+
+
+def test_general_kernels_tiny_images_and_batches(generic, oracle):
+    R = generic
+    for shape in ((1, 1), (1, 9), (9, 1), (2, 3), (5, 4), (33, 2)):
+        a = _img(oracle, 2300, shape[0], shape[1], 3, False)
+        d = R.Mat.empty()
+        R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, (9, 9), 2.0)
+        assert (d.to_numpy() == oracle.gaussian_blur(a, (9, 9), 2.0, 2.0)).all(), shape
+        f = _img(oracle, 2301, shape[0], shape[1], 1, True)
+        k = np.arange(25, dtype=np.float32).reshape(5, 5) / 25
+        R.imgproc.filter2d(R.Mat.from_numpy(f), d, k)
+        assert (d.to_numpy().view(np.int32) == oracle.filter2d(f, k, 0.0).view(np.int32)).all(), shape
+    # a batch of device frames: one launch, grid.z = frames
+    n, h, w = 3, 40, 500
+    frames = [_img(oracle, 2400 + j, h, w, 3, False) for j in range(n)]
+    src, dst = R.Mat.device_batch(n, h, w, 3), R.Mat.device_batch(n, h, w, 3)
+    import ctypes as C
+    from rustcv_b200 import _ffi as F
+    for j in range(n):
+        hm = R.Mat.from_numpy(frames[j])
+        F.check(F.lib.rcv_mat_upload(C.byref(hm.c()), C.byref(src[j].c())))
+    n0 = R.imgproc.launch_count()
+    R.imgproc.gaussian_blur_batch(src, dst, (13, 13), 2.0, 2.0)
+    assert R.imgproc.launch_count() - n0 == 1
+    for j in range(n):
+        assert (dst[j].to_numpy() == oracle.gaussian_blur(frames[j], (13, 13), 2.0, 2.0)).all(), f"frame {j}"
