@@ -68,9 +68,13 @@ struct Mat {
     return {data.data() + (size_t)row * step, (size_t)cols * channels * elem_size()};
   }
   // what VideoCapture::read does to its output before converting (videoio/mod.rs:192-199)
+  // A buffer that was page-locked in place (pin_in_place) is released before it is reallocated.
   void ensure_size(int32_t r, int32_t c, uint8_t cn, uint8_t d = U8) {
     size_t st = (size_t)c * cn * (d == F32 ? 4 : 1);
-    if (data.size() != (size_t)r * st) data.assign((size_t)r * st, 0);
+    if (data.size() != (size_t)r * st) {
+      if (!data.empty()) rcv_host_unregister(data.data());  // no-op when never registered
+      data.assign((size_t)r * st, 0);
+    }
     rows = r;
     cols = c;
     channels = cn;
@@ -90,6 +94,17 @@ struct Mat {
     return m;
   }
 };
+
+// The reference reuses one Vec<u8> per Mat frame after frame (videoio/mod.rs:192-199): page-lock it in place once
+// and every later call DMAs it directly (rcv_host_register).  `release` must run before the Mat is destroyed or
+// its buffer replaced by hand -- the Rust wrapper does it in Drop.
+inline Result pin_in_place(Mat &m) {
+  if (m.data.empty()) return Result();
+  return check(rcv_host_register(m.data.data(), m.data.size()));
+}
+inline void release(Mat &m) {
+  if (!m.data.empty()) rcv_host_unregister(m.data.data());
+}
 
 // Device-resident storage variant (HBM).  Move-only RAII, freed like the reference frees its
 // native handle in Drop (rustcv-camera/src/backend/macos/mod.rs:264-272).
@@ -135,6 +150,8 @@ class DeviceMat {
 }  // namespace core
 
 inline Result init(int device = 0) { return check(rcv_init(device)); }
+// every GPU of the box (or the first `ngpus`), one library worker thread per GPU
+inline Result init_multi(int ngpus = 0) { return check(rcv_init_multi(ngpus)); }
 
 namespace imgproc {
 using core::Mat;
@@ -170,6 +187,21 @@ inline Result gaussian_blur(const Mat &src, Mat &dst, Size ksize, double sigma_x
 inline Result gaussian_blur(const core::DeviceMat &src, core::DeviceMat &dst, Size ksize, double sigma_x,
                             double sigma_y = 0.0) {
   return check(rcv_gaussian_blur(&src.pod(), &dst.pod(), ksize.width, ksize.height, sigma_x, sigma_y));
+}
+
+// A batch of independent frames sharded over `ngpus` GPUs (0 = all initialised) from this ONE calling thread:
+// frame j runs on GPU j mod ngpus; returns when every frame is done.
+inline Result gaussian_blur_batch(const std::vector<Mat> &srcs, std::vector<Mat> &dsts, Size ksize, double sigma_x,
+                                  double sigma_y = 0.0, int ngpus = 0) {
+  dsts.resize(srcs.size());
+  std::vector<RcvMat> s(srcs.size()), d(srcs.size());
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    dsts[i].ensure_size(srcs[i].rows, srcs[i].cols, srcs[i].channels, srcs[i].depth);
+    s[i] = srcs[i].pod();
+    d[i] = dsts[i].pod();
+  }
+  return check(rcv_gaussian_blur_batch_multi(s.data(), d.data(), (int32_t)s.size(), ngpus, ksize.width, ksize.height, sigma_x,
+                                             sigma_y));
 }
 
 inline Result filter2d(const Mat &src, Mat &dst, const std::vector<float> &kernel, int kw, int kh, float delta = 0.f) {

@@ -115,6 +115,28 @@ int main(int argc, char **argv) {
     EXPECT(mag.rows == h && mag.cols == w && mag.channels == 1 && mag.depth == core::F32);
     EXPECT(mag.data == want.data);
   }
+  // the reference's reused Vec<u8>, page-locked in place once; then a batch fanned out over every GPU of the box
+  // from this one thread (frame j -> GPU j mod N)
+  {
+    EXPECT(init_multi(0).is_ok());
+    const int n = 5, h = 96, w = 160;
+    std::vector<core::Mat> srcs(n), dsts, wants(n);
+    for (int j = 0; j < n; ++j) {
+      srcs[j] = core::Mat::create(h, w, 3);
+      wants[j] = core::Mat::create(h, w, 3);
+      orc_fill_u8(40 + j, srcs[j].data.data(), srcs[j].data.size());
+      orc_gaussian_blur_u8(srcs[j].data.data(), srcs[j].step, wants[j].data.data(), wants[j].step, h, w, 3, 5, 5, 0.0, 0.0);
+    }
+    EXPECT(core::pin_in_place(srcs[0]).is_ok());
+    EXPECT(core::pin_in_place(srcs[0]).is_ok());  // idempotent
+    EXPECT(imgproc::gaussian_blur_batch(srcs, dsts, {5, 5}, 0.0, 0.0, 0).is_ok());
+    for (int j = 0; j < n; ++j) EXPECT(dsts[j].data == wants[j].data);
+    core::Mat one;
+    EXPECT(imgproc::gaussian_blur(srcs[0], one, {5, 5}, 0.0).is_ok());  // the registered Mat through the single-frame call
+    EXPECT(one.data == wants[0].data);
+    core::release(srcs[0]);
+    core::release(srcs[0]);
+  }
   std::puts("host_mirror ok");
   return 0;
 }
