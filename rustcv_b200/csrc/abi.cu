@@ -212,7 +212,7 @@ int copy_out_rows(const RcvMat *m, const Staged &st, int r0, int r1, cudaStream_
 int pick_host_band_rows(const RcvMat *src, const RcvMat *dst, const Banding &bd, bool bounce) {
   if (bd.halo < 0 || src->rows != dst->rows || src->rows <= 0) return 0;
   if (!is_host(src) && !is_host(dst)) return 0;
-  const int64_t band_bytes = bounce ? opt_get("host.bounce_band_bytes", 3 << 20) : opt_get("host.band_bytes", 6 << 20);
+  const int64_t band_bytes = bounce ? opt_get("host.bounce_band_bytes", 4 << 20) : opt_get("host.band_bytes", 6 << 20);
   if (band_bytes <= 0) return 0;
   size_t rb = mat_row_bytes(src) > mat_row_bytes(dst) ? mat_row_bytes(src) : mat_row_bytes(dst);
   if (rb == 0) return 0;

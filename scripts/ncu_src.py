@@ -21,7 +21,7 @@ for r in data:
     for i in stall_cols:
         stalls[hdr[i]] += int(r[i])
 print("total warp instr", tot, "per unit", round(tot / units, 1))
-for op, c in byop.most_common(28):
+for op, c in byop.most_common():
     print(f"{op:12s} {c:12d} {100 * c / tot:5.1f}%  per-unit {c / units:6.2f}  samples {samp[op]}")
 ts = sum(stalls.values())
 print([(k, round(100 * v / ts, 1)) for k, v in stalls.most_common(10)])

@@ -204,3 +204,61 @@ def test_new_entry_points_validate_before_cuda_and_refuse_without_a_gpu():
     assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, 2, C.byref(R.Mat.new(8, 8, 3).c())) == F.RCV_ERR_SIZE
     assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(R.Mat.new(8, 8, 1).c())) == F.RCV_ERR_DEPTH
     assert F.lib.rcv_mjpeg_to_bgr(jpeg.ctypes.data, jpeg.size, C.byref(R.Mat.new(8, 8, 3).c())) == F.RCV_ERR_NOT_INIT
+
+
+def test_round2_entry_points_validate_before_cuda_and_refuse_without_a_gpu():
+    """Multi-GPU batches, the coefficient broadcast, host registration: contracts checked before any CUDA call,
+    no fallback without an initialised B200."""
+    import rustcv_b200 as R
+    from rustcv_b200 import _ffi as F
+    from rustcv_b200.mat import MatBatch
+
+    a = [R.Mat.new(8, 8, 3) for _ in range(3)]
+    b = [R.Mat.new(8, 8, 3) for _ in range(3)]
+    sa, sb = MatBatch.of(a), MatBatch.of(b)
+    f = F.lib.rcv_gaussian_blur_batch_multi
+    assert f(sa.arr, sb.arr, 3, 0, 5, 5, 0.0, 0.0) == F.RCV_ERR_NOT_INIT
+    assert b"no CPU fallback" in F.lib.rcv_last_error()
+    assert f(None, None, 3, 0, 5, 5, 0.0, 0.0) == F.RCV_ERR_ARG
+    assert f(None, None, 0, 0, 5, 5, 0.0, 0.0) == F.RCV_OK
+    # every element of a batch is checked: geometry ...
+    odd = MatBatch.of([a[0], a[1], R.Mat.new(8, 9, 3)])
+    assert f(odd.arr, sb.arr, 3, 0, 5, 5, 0.0, 0.0) == F.RCV_ERR_SIZE
+    # ... and aliasing: dst[2] is src[0] (no op here runs in place; frames of a batch run concurrently)
+    alias = MatBatch.of([b[0], b[1], a[0]])
+    assert f(sa.arr, alias.arr, 3, 0, 5, 5, 0.0, 0.0) == F.RCV_ERR_ARG
+    assert F.lib.rcv_gaussian_blur_batch(sa.arr, alias.arr, 3, 5, 5, 0.0, 0.0) == F.RCV_ERR_ARG
+    # overlapping (not identical) buffers are in-place too
+    big = np.zeros(8 * 24 + 24, np.uint8)
+    s = R.Mat.new(8, 8, 3)
+    s.data = big[:192]
+    d = R.Mat.new(8, 8, 3)
+    d.data = big[24:216]
+    assert F.lib.rcv_cvt_color(C.byref(s.c()), C.byref(d.c()), F.COLOR_RGB2BGR) == F.RCV_ERR_ARG
+    assert F.lib.rcv_gaussian_blur(C.byref(s.c()), C.byref(d.c()), 3, 3, 0.0, 0.0) == F.RCV_ERR_ARG
+    # the fused YUYV -> GaussianBlur chain rejects odd widths (the blur would read an unconverted column)
+    assert F.lib.rcv_yuyv_to_bgr_gaussian5(C.byref(R.Mat.new(8, 9, 2).c()), C.byref(R.Mat.new(8, 9, 3).c())) == F.RCV_ERR_SIZE
+    # broadcast / registration / placement need an initialised GPU; argument errors come first
+    co = (C.c_float * 4)(1, 2, 3, 4)
+    assert F.lib.rcv_set_kernel_broadcast(None, 4, 0, 0, None) == F.RCV_ERR_ARG
+    assert F.lib.rcv_set_kernel_broadcast(co, 0, 0, 0, None) == F.RCV_ERR_ARG
+    assert F.lib.rcv_set_kernel_broadcast(co, 1000, 0, 0, None) == F.RCV_ERR_ARG
+    assert F.lib.rcv_set_kernel_broadcast(co, 4, 0, 0, None) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_host_register(None, 16) == F.RCV_ERR_ARG
+    assert F.lib.rcv_host_register(big.ctypes.data, big.size) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_host_unregister(big.ctypes.data) == F.RCV_OK  # nothing registered: nothing to undo
+    p = C.c_void_p()
+    assert F.lib.rcv_pinned_alloc_on(0, C.byref(p), 64) == F.RCV_ERR_NOT_INIT
+    assert F.lib.rcv_pinned_free(big.ctypes.data) == F.RCV_ERR_ARG  # not a pointer of rcv_pinned_alloc
+    taps = (C.c_int32 * 3)(64, 128, 64)
+    g = F.lib.rcv_sep_filter2d_q8_batch_multi
+    assert g(sa.arr, sb.arr, 3, 0, taps, 3, None, 3) == F.RCV_ERR_ARG  # kx without ky
+    assert g(sa.arr, sb.arr, 3, 0, None, 0, None, 3) == F.RCV_ERR_ARG  # bank taps need their counts
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_init_multi_fails_loudly_without_a_gpu():
+    from rustcv_b200 import _ffi as F
+
+    assert F.lib.rcv_init_multi(0) == F.RCV_ERR_CUDA
+    assert F.lib.rcv_init(-1) == F.RCV_ERR_CUDA  # RCV_DEVICE / GPU 0: still no GPU

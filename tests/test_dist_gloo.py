@@ -65,3 +65,9 @@ def test_shard_frames_covers_everything_once():
         for world in (1, 2, 4, 8):
             got = sorted(sum((bench.shard_frames(n, r, world) for r in range(world)), []))
             assert got == list(range(n))
+            # BASELINE configs 4 / 5: 256 / 64 frames over the ranks
+            assert sum(bench.frames_for_rank(n, r, world) for r in range(world)) == n
+    assert [bench.frames_for_rank(256, r, 8) for r in range(8)] == [32] * 8
+    assert [bench.frames_for_rank(64, r, 4) for r in range(4)] == [16] * 4
+    # both arms of bench.py describe the workload with the same config object
+    assert bench.config_dict(2, 32) == bench.config_dict(2, 32) and "workload" in bench.config_dict(1, 32)

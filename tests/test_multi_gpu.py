@@ -212,7 +212,7 @@ def test_pageable_single_frame_banded_bounce(rcv, oracle):
         got = dy.to_numpy()
         assert (got[:, :1918] == wanty[:, :1918]).all() and (got[:, 1918] == 0x5A).all()
     finally:
-        R.imgproc.set_option("host.bounce_band_bytes", 3 << 20)
+        R.imgproc.set_option("host.bounce_band_bytes", 4 << 20)
 
 
 def test_pageable_batch_and_unbandable_ops(rcv, oracle):
