@@ -328,19 +328,25 @@ class LinkProbe:
         return {"h2d_gbs": self._timed(True, False, reps), "d2h_gbs": self._timed(False, True, reps),
                 "duplex_gbs_each": self._timed(True, True, reps), "bytes_each_way": self.nbytes}
 
-    def all_ranks(self, world: int, reps: int = 5) -> dict:
+    def _all(self, up: bool, down: bool, reps: int) -> float:
         torch = self.torch
         best = 1e30
         for _ in range(reps):
             torch.cuda.synchronize(self.dev)
             barrier()
             t0 = time.perf_counter()
-            self._issue(True, True)
+            self._issue(up, down)
             torch.cuda.synchronize(self.dev)
             dt = time.perf_counter() - t0
             barrier()
             best = min(best, reduce_max(dt, device=self.dev))  # the slowest rank of this round
+        return best
+
+    def all_ranks(self, world: int, reps: int = 5) -> dict:
+        best = self._all(True, True, reps)
+        up, down = self._all(True, False, 3), self._all(False, True, 3)
         return {"duplex_gbs_each_total": world * self.nbytes / best / 1e9, "duplex_gbs_each_per_gpu": self.nbytes / best / 1e9,
+                "h2d_only_gbs_total": world * self.nbytes / up / 1e9, "d2h_only_gbs_total": world * self.nbytes / down / 1e9,
                 "ranks": world, "bytes_each_way_per_rank": self.nbytes,
                 "how": "all ranks at once, barrier-aligned, wall clock, slowest rank, best of %d" % reps}
 
@@ -421,7 +427,7 @@ class Extra:
 
     def cfg3(self):
         R, O = self.R, self.O
-        n, h, w = 64, 1080, 1920
+        n, h, w = 128, 1080, 1920  # 1.06 GB in + 1.06 GB out per launch: ramp and tail of a launch are ~10 us whatever its size
         src, dst = R.Mat.device_batch(n, h, w, 1, R.F32), R.Mat.device_batch(n, h, w, 1, R.F32)
         base = O.fill_f32(3, h * w)
         self.fill(src, [np.roll(base, i * 31).reshape(h, w) for i in range(8)])
@@ -431,7 +437,7 @@ class Extra:
         O.set_threads(1)
         got = dst[0].to_numpy()
         ulp = int(np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max())
-        rec = self.record("cfg3 Sobel3x3+magnitude 1920x1080 f32, 64 frames per launch", ms, steps, clk, n * h * w, 8, "pix",
+        rec = self.record("cfg3 Sobel3x3+magnitude 1920x1080 f32, 128 frames per launch", ms, steps, clk, n * h * w, 8, "pix",
                           "k_strip<Sobel3Op<0>>", {"parity": {"frame0_max_ulp_vs_oracle": ulp}})
         src.free(); dst.free()
         return rec
@@ -809,9 +815,9 @@ def main() -> None:
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("frames_per_launch") == F_:
-                traffic = tj.get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))  # one ncu --set full capture of a 32-frame launch: DRAM bytes per frame x F
+            if tj.get("frames_per_launch"):
+                traffic = tj.get("dram_bytes_per_launch") / tj["frames_per_launch"] * F_
         each_way = e2e_value * 1e6 * CN / 1e9  # GB/s each way, all ranks together
         if clocks and (clocks.get("samples") or 0) == 0:
             clocks = all_clocks  # the 5 ms burst fell between two samples: report the run's

@@ -138,9 +138,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   const uint32_t tiles = smem_u32(smem_raw) + (uint32_t)warp * S * kStageBytes;
   const uint32_t bars = smem_u32(smem_raw) + (uint32_t)NW * S * kStageBytes + (uint32_t)warp * S * 8;
 
-  // Two work counters alternate between launches: this launch claims from one and clears the other,
-  // which the next launch on the (single, in-order) library stream will use -- no memset node.
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_item != nullptr) *p.reset_item = 0ULL;
+  // Programmatic dependent launch: the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization, so the
+  // NEXT kernel of the stream may be scheduled as soon as this grid's CTAs have started (its CTAs become resident
+  // as ours exit) and runs its prologue -- launch latency, parameter / tensor-map fetch, mbarrier set-up -- under
+  // our tail.  Nothing below griddepcontrol.wait (global reads, stores, the work counters) happens before the
+  // previous grid has completed and flushed.  Without the attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;");
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(bars + s * 8, 1);
@@ -148,6 +151,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     fence_proxy_async();
   }
   __syncwarp();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Two work counters alternate between launches: this launch claims from one and clears the other,
+  // which the next launch on the (single, in-order) library stream will use -- no memset node.
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_item != nullptr) *p.reset_item = 0ULL;
 
   uint32_t phase = 0;  // bit s = parity the next wait on stage s must see
   const long long total_warps = (long long)gridDim.x * NW;
@@ -432,7 +439,21 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     p.next_item = (unsigned long long *)ctr + which;
     p.reset_item = (unsigned long long *)ctr + (which ^ 1u);
   }
-  kern<<<grid, NW * 32, smem, s>>>(*tmap, p);
+  if (opt_get("strip.pdl", 1) != 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RCV_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmap, p));
+  } else {
+    kern<<<grid, NW * 32, smem, s>>>(*tmap, p);
+  }
   count_launch();
   RCV_CUDA(cudaGetLastError());
   return RCV_OK;

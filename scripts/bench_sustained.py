@@ -33,6 +33,24 @@ for i in range(F_):
 sampler = bench.ClockSampler(0)
 sampler.start()
 OP = os.environ.get("OP", "gauss5")
+NF = int(os.environ.get("NF", "64"))
+GB = 6 * F_ * ROWS * COLS / 1e9  # algorithmic bytes per step
+if OP == "sobel":
+    src.free(); dst.free()
+    src, dst = R.Mat.device_batch(NF, 1080, 1920, 1, R.F32), R.Mat.device_batch(NF, 1080, 1920, 1, R.F32)
+    hf = R.Mat.from_numpy(O.fill_f32(3, 1080 * 1920).reshape(1080, 1920))
+    for i in range(NF):
+        F.check(F.lib.rcv_mat_upload(C.byref(hf.c()), C.byref(src[i].c())))
+    GB = 8 * NF * 1080 * 1920 / 1e9
+if OP == "warp":
+    src.free(); dst.free()
+    NF = int(os.environ.get("NF", "16"))
+    src, dst = R.Mat.device_batch(NF, 4096, 4096, 1, R.F32), R.Mat.device_batch(NF, 4096, 4096, 1, R.F32)
+    hf = R.Mat.from_numpy(O.fill_f32(5, 4096 * 4096).reshape(4096, 4096))
+    for i in range(NF):
+        F.check(F.lib.rcv_mat_upload(C.byref(hf.c()), C.byref(src[i].c())))
+    GB = 7.6 * NF * 4096 * 4096 / 1e9
+    WM = R.imgproc.get_rotation_matrix_2d(((4096 - 1) / 2, (4096 - 1) / 2), 15.0)
 
 
 def step():
@@ -44,6 +62,10 @@ def step():
         R.imgproc.gaussian_blur_batch(src, dst, (5, 5), 1.0, 1.0)
     elif OP == "swap":
         R.imgproc.cvt_color_batch(src, dst, R.imgproc.COLOR_RGB2BGR)
+    elif OP == "sobel":
+        R.imgproc.sobel_mag_batch(src, dst)
+    elif OP == "warp":
+        R.imgproc.warp_affine_batch(src, dst, WM)
 
 
 for setting in (sys.argv[1:] or ["default"]):
@@ -77,7 +99,7 @@ for setting in (sys.argv[1:] or ["default"]):
     ms = e0.elapsed_time(e1) / n
     clk = sampler.window(t0 + 0.3, t1)
     ok = O.crc32(dst[0].to_numpy()) == 0x827081C8 if OP == "gauss5" else None
-    gb = 6 * F_ * ROWS * COLS / 1e9
+    gb = GB
     print(json.dumps({"op": OP, "setting": setting, "burst_ms": round(burst_ms, 4), "burst_frac": round(gb / (burst_ms * 1e-3) / PEAK, 4),
                       "sustained_ms": round(ms, 4), "sustained_frac": round(gb / (ms * 1e-3) / PEAK, 4), "sm_mhz": clk.get("sm_mhz"),
                       "power_w_max": clk.get("power_w_max"), "reasons": clk.get("reasons"), "parity": ok}), flush=True)
