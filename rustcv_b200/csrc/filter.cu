@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant
   // stage 1: raw[r][x] = src[reflect(y0 + r - ry)][reflect column of x]; the reflected source offset of every
   // raw-tile column is computed once per thread (no divisions in the row loop)
   constexpr int NX = (kSepMaxRW + 31) / 32;
+  const bool interior_x = ex0 - rx * a.cn >= 0 && ex0 - rx * a.cn + RW <= ncols;
   int xoff[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
@@ -155,8 +156,12 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant
     xoff[i] = 0;
     if (x < RW) {
       const int ex = ex0 + x - rx * a.cn;
-      const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);  // floor division
-      xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+      if (interior_x) {  // the tile's columns and halo lie inside the row: no reflection, no division
+        xoff[i] = ex;
+      } else {
+        const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);  // floor division
+        xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+      }
     }
   }
   for (int r = warp; r < RH; r += NWARP) {
@@ -498,6 +503,7 @@ __global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
   uint8_t *dst = a.dst + (size_t)blockIdx.z * a.dfs;
   for (int i = threadIdx.x; i < kw * kh; i += kF2dThreads) taps[i] = a.taps[i];
   constexpr int NX = (kF2dMaxRW + 31) / 32;
+  const bool interior_x = ex0 - rx * a.cn >= 0 && ex0 - rx * a.cn + RW <= ncols;
   int xoff[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
@@ -505,8 +511,12 @@ __global__ void __launch_bounds__(kF2dThreads) k_filter2d(const F2dArgs a) {
     xoff[i] = 0;
     if (x < RW) {
       const int ex = ex0 + x - rx * a.cn;
-      const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
-      xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+      if (interior_x) {
+        xoff[i] = ex;
+      } else {
+        const int px = ex >= 0 ? ex / a.cn : -((-ex + a.cn - 1) / a.cn);
+        xoff[i] = reflect101(px, a.cols) * a.cn + (ex - px * a.cn);
+      }
     }
   }
   for (int r = warp; r < RH; r += NWARP) {

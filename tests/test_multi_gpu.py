@@ -308,3 +308,73 @@ def test_rcv_device_env_selects_the_gpu():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
     assert out.returncode == 0, out.stderr
     assert f"device {want}" in out.stdout
+
+
+# ---- a library, not a script: concurrent callers, lifecycle ----------------------------------------------------------
+def test_concurrent_callers_on_distinct_mats(rcv, oracle):
+    """The header's thread contract: re-entrant and thread-safe for distinct Mats (pageable, registered and device
+    Mats, single calls and batches, from several threads at once)."""
+    import threading
+
+    R = rcv
+    rows, cols = 300, 420
+    errs = []
+
+    def worker(seed, kind):
+        try:
+            for it in range(4):
+                img = oracle.fill_u8(seed * 10 + it, rows * cols * 3).reshape(rows, cols, 3)
+                want = oracle.gaussian_blur(img, (5, 5))
+                if kind == "host":
+                    d = R.Mat.empty()
+                    R.imgproc.gaussian_blur(R.Mat.from_numpy(img), d, (5, 5), 0.0)
+                elif kind == "registered":
+                    s = R.Mat.from_numpy(img).register()
+                    d = R.Mat.new(rows, cols, 3).register()
+                    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+                    s.unregister(); d.unregister()
+                elif kind == "device":
+                    s = R.Mat.from_numpy(img).upload()
+                    d = s.like()
+                    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)
+                else:  # a multi-GPU batch of three copies
+                    srcs = [R.Mat.from_numpy(img) for _ in range(3)]
+                    dsts = [R.Mat.new(rows, cols, 3) for _ in range(3)]
+                    R.imgproc.gaussian_blur_batch_multi(srcs, dsts, 0, (5, 5), 0.0, 0.0)
+                    d = dsts[2]
+                if not (d.to_numpy() == want).all():
+                    errs.append(f"{kind} seed {seed} iteration {it}: mismatch")
+        except Exception as e:  # noqa: BLE001
+            errs.append(f"{kind}: {type(e).__name__}: {e}")
+
+    R.imgproc.init_multi(0)
+    threads = [threading.Thread(target=worker, args=(i, k)) for i, k in enumerate(["host", "registered", "device", "multi", "host", "device"])]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errs, errs
+
+
+def test_shutdown_and_reinit_in_a_fresh_process():
+    """rcv_shutdown joins the worker / drain threads, frees contexts and registrations; the library can be
+    initialised again afterwards (run in a subprocess: the session fixture keeps its own context)."""
+    code = ("import numpy as np, rustcv_b200 as R\n"
+            "from oracle import pyoracle as O\n"
+            "img = O.fill_u8(7, 200 * 300 * 3).reshape(200, 300, 3)\n"
+            "want = O.gaussian_blur(img, (5, 5))\n"
+            "for cycle in range(3):\n"
+            "    R.imgproc.init_multi(0)\n"
+            "    s = R.Mat.from_numpy(img).register()\n"
+            "    d = R.Mat.empty()\n"
+            "    R.imgproc.gaussian_blur(s, d, (5, 5), 0.0)\n"
+            "    assert (d.to_numpy() == want).all()\n"
+            "    ds = [R.Mat.new(200, 300, 3) for _ in range(4)]\n"
+            "    R.imgproc.gaussian_blur_batch_multi([s] * 4, ds, 0, (5, 5), 0.0, 0.0)\n"
+            "    assert all((x.to_numpy() == want).all() for x in ds)\n"
+            "    s._registered = None  # shutdown drops caller registrations itself\n"
+            "    R.imgproc.shutdown()\n"
+            "print('cycles ok')\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert out.returncode == 0 and "cycles ok" in out.stdout, out.stdout + out.stderr
