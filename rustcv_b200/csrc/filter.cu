@@ -115,12 +115,15 @@ __device__ __forceinline__ void tap_chain(Acc (&acc)[N], const Tap *__restrict__
 // lanes of a warp that work on a tile row: a lane owns one channel of a block of N pixels, so only whole pixels
 constexpr int tile_lanes(int cn) { return 32 / cn * cn; }
 
-constexpr int kSepTBY = 32, kSepThreads = 256, kSepN = 8;  // tile rows; outputs per thread per pass
-constexpr int kSepMaxTBX = 32 * kSepN;                     // tile width in element columns (240 for 3 channels)
+// Outputs per thread: 8 rows in the vertical pass, 8 pixels in the horizontal pass.  (9 pixels would spread a
+// warp's lanes over distinct shared-memory banks -- see kF2dN -- but the wider tile costs a resident CTA per SM here:
+// measured slower for u8 and for 3-channel f32, profiles/r2_generic_kernels.txt.)
+constexpr int kSepTBY = 32, kSepThreads = 256, kSepN = 8, kSepNH = 8;
+constexpr int kSepMaxTBX = 32 * kSepNH;                    // tile width in element columns (270 for 3 channels)
 constexpr int kSepMaxRW = kSepMaxTBX + (kMaxTaps - 1) * 4;  // widest raw tile row (elements)
 
-// Stage 2 (horizontal): warp w takes tile rows w, w+8, ...; a lane computes the kSepN outputs of ONE channel of a
-// block of kSepN pixels (element columns x0 + m*cn) from the kw + kSepN - 1 raw values x0 + i*cn.
+// Stage 2 (horizontal): warp w takes tile rows w, w+8, ...; a lane computes the kSepNH outputs of ONE channel of a
+// block of kSepNH pixels (element columns x0 + m*cn) from the kw + kSepNH - 1 raw values x0 + i*cn.
 // Stage 3 (vertical): a thread computes kSepN consecutive rows of one element column from kh + kSepN - 1 values of
 // the horizontally filtered tile.
 template <typename T, int KN>
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant
   const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
   const int rx = kw / 2, ry = kh / 2;
   const int lanes = 32 / a.cn * a.cn;
-  const int TBX = lanes * kSepN;           // tile width (element columns)
+  const int TBX = lanes * kSepNH;          // tile width (element columns)
   const int RW = TBX + (kw - 1) * a.cn;    // raw tile width (elements)
   const int RH = kSepTBY + kh - 1;         // raw tile height
   T *raw = (T *)smem;
@@ -176,22 +179,22 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant
   __syncthreads();
   // stage 2: horizontal
   if (lane < lanes) {
-    const int x0 = lane / a.cn * (kSepN * a.cn) + lane % a.cn;
+    const int x0 = lane / a.cn * (kSepNH * a.cn) + lane % a.cn;
     for (int r = warp; r < RH; r += NWARP) {
       const T *p = raw + r * RW + x0;
-      Acc acc[kSepN];
+      Acc acc[kSepNH];
 #pragma unroll
-      for (int m = 0; m < kSepN; ++m) acc[m] = 0;
+      for (int m = 0; m < kSepNH; ++m) acc[m] = 0;
       const int cn = a.cn;
       if (sizeof(T) == 1)
-        tap_chain<kSepN, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
-                             [](Tap k, Acc v, Acc c) { return (Acc)(c + (Acc)k * v); });
+        tap_chain<kSepNH, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
+                              [](Tap k, Acc v, Acc c) { return (Acc)(c + (Acc)k * v); });
       else
-        tap_chain<kSepN, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
-                             [](Tap k, Acc v, Acc c) { return (Acc)fmaf((float)k, (float)v, (float)c); });
+        tap_chain<kSepNH, KN>(acc, (const Tap *)a.kx, kw, [&](int i) { return (Acc)p[i * cn]; },
+                              [](Tap k, Acc v, Acc c) { return (Acc)fmaf((float)k, (float)v, (float)c); });
       Acc *o = mid + r * TBX + x0;
 #pragma unroll
-      for (int m = 0; m < kSepN; ++m) o[m * cn] = acc[m];
+      for (int m = 0; m < kSepNH; ++m) o[m * cn] = acc[m];
     }
   }
   __syncthreads();
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(kSepThreads) k_sepfilter(const __grid_constant
 template <typename T, int KN>
 static int launch_sep_kn(const SepArgs<T> &a, int n, cudaStream_t s) {
   const int kw = KN > 0 ? KN : a.kw, kh = KN > 0 ? KN : a.kh;
-  const int TBX = tile_lanes(a.cn) * kSepN;
+  const int TBX = tile_lanes(a.cn) * kSepNH;
   const int RW = TBX + (kw - 1) * a.cn, RH = kSepTBY + kh - 1;
   const size_t smem = (((size_t)RW * RH * sizeof(T) + 15) & ~(size_t)15) + (size_t)TBX * RH * 4;
   auto kern = k_sepfilter<T, KN>;
@@ -479,7 +482,10 @@ struct F2dArgs {
   float delta;
 };
 
-constexpr int kF2dTBY = 32, kF2dThreads = 256, kF2dN = 8;
+// 9 outputs per lane, not 8: a lane's first column is (lane / cn) * 9 * cn + lane % cn, and with an odd 9 the lanes of
+// a warp fall into distinct shared-memory banks for 1, 2 and 4 channels (2-way at worst for 3) where 8 gave 3- to 8-way
+// conflicts on every read of the f32 tile (dense 5x5 f32 BGR 0.18 -> 0.24 of the roofline, u8 7x7 0.046 -> 0.059)
+constexpr int kF2dTBY = 32, kF2dThreads = 256, kF2dN = 9;
 constexpr int kF2dMaxRW = 32 * kF2dN + (kMaxTaps - 1) * 4;
 
 // A lane computes the kF2dN outputs of one channel of a block of kF2dN pixels of one tile row: kernel row by kernel
