@@ -357,7 +357,7 @@ int run_host_pipeline(Ctx *c, const RcvMat *srcs, RcvMat *dsts, int n, F &launch
     Staged in = si[k], out = so[k];
     if (!in.staged) in.v = view_of(&srcs[i], srcs[i].data, srcs[i].step);
     if (!out.staged) out.v = view_of(&dsts[i], dsts[i].data, dsts[i].step);
-    const bool sbounce = in.staged && (i == 0 ? !host_dma_ok(&srcs[0]) : !host_dma_ok(&srcs[i]));
+    const bool sbounce = in.staged && !host_dma_ok(&srcs[i]);
     const bool dbounce = out.staged && !host_dma_ok(&dsts[i]);
     // inside a batch the frames themselves overlap and bands only add hand-offs (measured, 16 pinned 4K frames:
     // 8.85 ms unbanded, 9.51 ms with the first and last frame banded, 9.9 ms with every frame banded): bands are

@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -36,9 +37,15 @@ struct MultiJoin {
   std::mutex mu;
   std::condition_variable cv;
   int pending = 0;
+  std::atomic<int> refs{0};  // the waiter + one per job: whoever lets go last frees it (never while a worker is still
+                             // inside mu's unlock path)
   std::vector<int> rc;
   std::vector<std::string> err;
 };
+
+static void multi_release(MultiJoin *j) {
+  if (j->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) delete j;
+}
 
 namespace {
 struct Job {
@@ -72,10 +79,13 @@ struct Worker {
         q.pop_front();
       }
       const int rc = j.fn(j.arg);
-      std::lock_guard<std::mutex> lk(j.join->mu);
-      j.join->rc[j.slot] = rc;
-      if (rc != RCV_OK) j.join->err[j.slot] = last_error();
-      if (--j.join->pending == 0) j.join->cv.notify_all();
+      {
+        std::lock_guard<std::mutex> lk(j.join->mu);
+        j.join->rc[j.slot] = rc;
+        if (rc != RCV_OK) j.join->err[j.slot] = last_error();
+        if (--j.join->pending == 0) j.join->cv.notify_all();
+      }
+      multi_release(j.join);
     }
   }
 };
@@ -100,6 +110,7 @@ Worker *worker_for(int device) {
 MultiJoin *multi_begin(int njobs) {
   MultiJoin *j = new MultiJoin();
   j->pending = njobs;
+  j->refs.store(njobs + 1);
   j->rc.assign(njobs, RCV_OK);
   j->err.assign(njobs, std::string());
   return j;
@@ -108,10 +119,13 @@ MultiJoin *multi_begin(int njobs) {
 void multi_submit(MultiJoin *j, int device, int slot, int (*fn)(void *), void *arg) {
   Worker *w = worker_for(device);
   if (!w) {
-    std::lock_guard<std::mutex> lk(j->mu);
-    j->rc[slot] = RCV_ERR_ARG;
-    j->err[slot] = "no worker for this device";
-    if (--j->pending == 0) j->cv.notify_all();
+    {
+      std::lock_guard<std::mutex> lk(j->mu);
+      j->rc[slot] = RCV_ERR_ARG;
+      j->err[slot] = "no worker for this device";
+      if (--j->pending == 0) j->cv.notify_all();
+    }
+    multi_release(j);
     return;
   }
   {
@@ -133,7 +147,7 @@ int multi_wait(MultiJoin *j) {
         break;
       }
   }
-  delete j;
+  multi_release(j);
   return rc;
 }
 
