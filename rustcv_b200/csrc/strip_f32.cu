@@ -162,9 +162,15 @@ struct Filter2dF32Op {
   }
 };
 
-// separable f32, single channel, kw == kh in {3, 5, 7}; RCV_ERR_UNSUPPORTED otherwise
+int launch_sepf32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
+                          cudaStream_t s);
+int launch_filter2d_f32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
+                                cudaStream_t s);
+
+// separable f32, kw == kh in {3, 5, 7}: single channel here, 2..4 channels in strip_f32cn.cu; RCV_ERR_UNSUPPORTED otherwise
 int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
                         cudaStream_t s) {
+  if (src.v.cn > 1) return launch_sepf32cn_strip(c, src, dst, kx, kw, ky, kh, s);
   if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
   float taps[14];
   if (kw != 3 && kw != 5 && kw != 7) return RCV_ERR_UNSUPPORTED;
@@ -180,6 +186,7 @@ int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const floa
 // dense f32, single channel, 3x3 or 5x5
 int launch_filter2d_f32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
                               cudaStream_t s) {
+  if (src.v.cn > 1) return launch_filter2d_f32cn_strip(c, src, dst, k, kw, kh, delta, s);
   if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
   if (kw != 3 && kw != 5) return RCV_ERR_UNSUPPORTED;
   float taps[26];

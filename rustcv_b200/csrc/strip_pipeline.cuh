@@ -97,6 +97,8 @@ __device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
 //             per item where the row's edges are: op.edges(left_edge, right_edge, xr, lane);
 //   Op::MACRO horizontal border elements are macro-pixels reflected INCLUDING the edge element
 //             (element -1 <- element 0, element n <- element n-1) instead of REFLECT_101.
+//   Op::HALO_LANES  halo lanes per side (default 1): an op whose horizontal reach P*E exceeds 16 bytes (multi-channel
+//             f32) gives up more lanes -- 2 halo lanes per side leave 448 output bytes per 512-byte tile row.
 template <class Op, class = void>
 struct OpOmul { static constexpr int value = 1; };
 template <class Op>
@@ -118,6 +120,16 @@ struct OpBandRows { static constexpr int value = 5 * 8 - 2 * Op::HV; };  // 40 f
 template <class Op>
 struct OpBandRows<Op, std::void_t<decltype(Op::BAND_ROWS)>> { static constexpr int value = Op::BAND_ROWS; };
 template <class Op, class = void>
+struct OpHaloLanes {  // Op::HALO_LANES: 16-byte halo lanes on EACH side of the strip
+  static constexpr int value = 1;
+  static constexpr bool declared = false;
+};
+template <class Op>
+struct OpHaloLanes<Op, std::void_t<decltype(Op::HALO_LANES)>> {
+  static constexpr int value = Op::HALO_LANES;
+  static constexpr bool declared = true;
+};
+template <class Op, class = void>
 struct OpMacro { static constexpr int value = 0; };
 template <class Op>
 struct OpMacro<Op, std::void_t<decltype(Op::MACRO)>> { static constexpr int value = Op::MACRO; };
@@ -128,7 +140,10 @@ struct OpMacro<Op, std::void_t<decltype(Op::MACRO)>> { static constexpr int valu
 template <class Op, int R, int S, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CUtensorMap tmap, const StripParams p) {
   static_assert(R == 8 && R >= 2 * Op::HV + 1, "chunk rows (the ops' window rotation assumes 8-row chunks)");
-  static_assert(Op::E * (Op::P + 1) <= 16, "horizontal halo must fit the 16-byte halo lanes");
+  constexpr int HL = OpHaloLanes<Op>::value;
+  constexpr int kHalo = HL * kLaneBytes, kOut = kTileBytes - 2 * kHalo;  // halo bytes per side, output bytes per tile row
+  static_assert(Op::E * Op::P <= kHalo && (OpHaloLanes<Op>::declared || Op::E * (Op::P + 1) <= 16),
+                "horizontal halo must fit the halo lanes");
   constexpr int HV = Op::HV, P = Op::P, E = Op::E;
   constexpr int OM = OpOmul<Op>::value, OD = OpOdiv<Op>::value, RO = OpMacro<Op>::value;
   constexpr uint32_t kStageBytes = R * kTileBytes;
@@ -173,24 +188,24 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     const unsigned t = it32 / (unsigned)p.strips;
     const int band = (int)(t % (unsigned)p.bands);
     const int frame = (int)(t / (unsigned)p.bands);
-    const int x0 = strip * kOutBytes;
+    const int x0 = strip * kOut;
     const int y0 = p.row_begin + band * p.band_rows;
     const int y1 = min(y0 + p.band_rows, p.row_end);
     const int ys = y0 - HV;                // first row fed
     const int n_feed = (y1 - y0) + 2 * HV;  // rows fed: ys .. y1+HV-1
     const int n_chunks = (n_feed + R - 1) / R;
-    const int cx = (x0 - kLaneBytes) >> 2;  // word coordinate of the tile (may be -4)
+    const int cx = (x0 - kHalo) >> 2;  // word coordinate of the tile (negative in the first strip)
     const bool left_edge = (x0 == 0);
-    const bool right_edge = (p.row_bytes < x0 + kOutBytes + kLaneBytes);
-    const int xr = kLaneBytes + (p.row_bytes - x0);  // tile byte offset of the first byte past the row
+    const bool right_edge = (p.row_bytes < x0 + kOut + kHalo);
+    const int xr = kHalo + (p.row_bytes - x0);  // tile byte offset of the first byte past the row
     const bool top = (ys < 0);
     const bool bottom = (y1 + HV > p.rows);  // the fed rows run past the last image row
     const bool fast_strip = p.vec_store != 0 && !right_edge;  // full 16-byte stores in lanes 1..30
 
     // this lane's slice of the outputs
-    const int xl = x0 + (lane - 1) * kLaneBytes;
+    const int xl = x0 + (lane - HL) * kLaneBytes;
     int nvalid = 0;
-    if (lane >= 1 && lane <= 30) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes) * OM / OD;  // in OUTPUT bytes
+    if (lane >= HL && lane <= 31 - HL) nvalid = min(max(p.row_bytes - xl, 0), kLaneBytes) * OM / OD;  // in OUTPUT bytes
     // output pointers of the next row to emit (row y0), advanced by one step per emitted row
     uint8_t *optr[3];
 #pragma unroll
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
 #pragma unroll
             for (int k = 1; k <= P; ++k)
 #pragma unroll
-              for (int b = 0; b < E; ++b) sts8(row + kLaneBytes - k * E + b, lds8(row + kLaneBytes + (k - RO) * E + b));
+              for (int b = 0; b < E; ++b) sts8(row + kHalo - k * E + b, lds8(row + kHalo + (k - RO) * E + b));
           }
           if (right_edge) {
 #pragma unroll
@@ -404,7 +419,7 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     if (p.row_end <= p.row_begin) return RCV_OK;
   }
   p.row_bytes = (int)src.v.row_bytes();
-  p.strips = ceil_div(p.row_bytes, kOutBytes);
+  p.strips = ceil_div(p.row_bytes, kTileBytes - 2 * OpHaloLanes<Op>::value * kLaneBytes);
   p.band_rows = pick_band_rows(c, band_opt, p.row_end - p.row_begin, p.strips, src.n, Op::HV, NW, OpBandRows<Op>::value);
   p.bands = ceil_div(p.row_end - p.row_begin, p.band_rows);
   p.n_frames = src.n;

@@ -120,11 +120,24 @@ f = batch(NF, FH, FW, 1, R.F32, seed=3)
 fo = R.Mat.device_batch(NF, FH, FW, 1, R.F32)
 run("Sobel 3x3 + magnitude, 1080p f32 x128 [k_strip<Sobel3Op<0>>]", lambda: I.sobel_mag_batch(f, fo), 8 * NF * FH * FW)
 for ks in (3, 5, 7):
-    def sep(ks=ks):
-        for i in range(16):
-            I.gaussian_blur(f[i], fo[i], (ks, ks), 1.2)
-    run(f"GaussianBlur {ks}x{ks} sigma 1.2, 1080p gray f32, 16 launches of 1 frame [k_strip<SepF32Op<{ks}>>]", sep, 8 * 16 * FH * FW)
+    run(f"GaussianBlur {ks}x{ks} sigma 1.2, 1080p gray f32 x128 [k_strip<SepF32Op<{ks}>>]", lambda: I.gaussian_blur_batch(f, fo, (ks, ks), 1.2, 1.2), 8 * NF * FH * FW)
 f.free(); fo.free()
+f3 = batch(32, FH, FW, 3, R.F32, seed=3)
+fo3 = R.Mat.device_batch(32, FH, FW, 3, R.F32)
+for ks in (3, 5, 7):
+    run(f"GaussianBlur {ks}x{ks} sigma 1.2, 1080p BGR f32 x32 [k_strip<SepF32CnOp<{ks},3>>]", lambda: I.gaussian_blur_batch(f3, fo3, (ks, ks), 1.2, 1.2), 24 * 32 * FH * FW)
+run("GaussianBlur 11x11 sigma 2, 1080p BGR f32 x32 [k_sepfilter<f32,11>]", lambda: I.gaussian_blur_batch(f3, fo3, (11, 11), 2.0, 2.0), 24 * 32 * FH * FW)
+
+
+def f2df(k):
+    for i in range(8):
+        I.filter2d(f3[i], fo3[i], k)
+
+
+run("filter2D 3x3, 1080p BGR f32, 8 launches of 1 frame [k_strip<Filter2dF32CnOp<3,3>>]", lambda: f2df(k3), 24 * 8 * FH * FW)
+run("filter2D 5x5, 1080p BGR f32, 8 launches of 1 frame [k_strip<Filter2dF32CnOp<5,3>>]", lambda: f2df(np.ones((5, 5), np.float32) / 25), 24 * 8 * FH * FW)
+run("filter2D 7x7, 1080p BGR f32, 8 launches of 1 frame [k_filter2d<f32,7>]", lambda: f2df(np.ones((7, 7), np.float32) / 49), 24 * 8 * FH * FW)
+f3.free(); fo3.free()
 y8 = batch(32, FH, FW, 2, seed=6)
 mg = R.Mat.device_batch(32, FH, FW, 1, R.F32)
 run("chain YUYV->BGR->Gray->f32->Sobel magnitude, 1080p x32 [k_strip<YuyvSobelOp>]", lambda: I.yuyv_to_sobel_mag_batch(y8, mg), 6 * 32 * FH * FW)
