@@ -802,11 +802,19 @@ int rcv_convert_to(const RcvMat *src, RcvMat *dst, double alpha, double beta) {
 }
 
 // ---- filters -------------------------------------------------------------------------------
+// rows of source a band of the banded host pipeline needs above / below itself: half the vertical kernel size the
+// launcher will derive (cv::GaussianBlur: kh <= 0 means "from sigma")
+static int gaussian_halo_rows(const RcvMat *src, int kh, double sigma_x, double sigma_y) {
+  if (sigma_y <= 0) sigma_y = sigma_x;
+  if (kh <= 0 && sigma_y > 0) kh = gaussian_ksize(sigma_y, src->depth == RCV_U8);
+  return kh > 0 ? kh / 2 : 0;
+}
+
 int rcv_gaussian_blur(const RcvMat *src, RcvMat *dst, int32_t kw, int32_t kh, double sigma_x, double sigma_y) {
   RCV_TRY(check_filter_pair(src, dst, "GaussianBlur"));
   return run_unary(src, dst, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
-  }, -1, band_window(3));
+  }, -1, band_window(gaussian_halo_rows(src, kh, sigma_x, sigma_y)));
 }
 
 static int gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t kw, int32_t kh, double sigma_x,
@@ -816,7 +824,7 @@ static int gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int3
   RCV_TRY(check_filter_pair(&srcs[0], &dsts[0], "GaussianBlur"));
   return run_batch(srcs, dsts, n, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
     return launch_gaussian(c, s, d, kw, kh, sigma_x, sigma_y, st);
-  }, -1, band_window(3), ngpus);
+  }, -1, band_window(gaussian_halo_rows(&srcs[0], kh, sigma_x, sigma_y)), ngpus);
 }
 int rcv_gaussian_blur_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t kw, int32_t kh, double sigma_x,
                             double sigma_y) {

@@ -305,7 +305,7 @@ static bool strip_taps_ok(const int32_t *k, int n) {
 // ops, any other symmetric 3 / 5 / 7 taps GaussQ8Op), else the general kernel.
 int launch_sepfilter_q8(Ctx *c, const DBatch &src, const DBatch &dst, const int32_t *kx, int kw, const int32_t *ky,
                         int kh, cudaStream_t s) {
-  if (kw == kh && (kw == 3 || kw == 5 || kw == 7) && opt_get("gauss.force_generic", 0) == 0 && strip_taps_ok(kx, kw) &&
+  if (kw == kh && (kw & 1) && kw >= 3 && kw <= 15 && opt_get("gauss.force_generic", 0) == 0 && strip_taps_ok(kx, kw) &&
       strip_taps_ok(ky, kh) && src.v.rows > 0 && src.v.cols > 0 && src.n > 0) {
     const bool binomial5 = kw == 5 && kx[0] == 16 && kx[1] == 64 && kx[2] == 96 && ky[0] == 16 && ky[1] == 64 && ky[2] == 96;
     if (binomial5) {

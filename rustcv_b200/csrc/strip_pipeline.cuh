@@ -62,6 +62,7 @@ struct StripParams {
   unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
   unsigned long long *reset_item; // the OTHER counter of the pair: zeroed here for the next launch on this stream
   uint32_t taps_x[4], taps_y[4];  // GaussQ8Op: symmetric Q8 taps, [0] outermost .. [KS/2] centre
+  uint32_t wtaps[16];             // GaussQ8WideOp (9..15 taps): x taps [0..7], y taps [8..15], same order
   float ftaps[52];                // SepF32Op: kx[0..KS) then ky[0..KS); Filter2dOp: KS*KS taps row-major, then delta
 };
 
@@ -139,7 +140,9 @@ struct OpMacro<Op, std::void_t<decltype(Op::MACRO)>> { static constexpr int valu
 // ---------------------------------------------------------------------------------------
 template <class Op, int R, int S, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CUtensorMap tmap, const StripParams p) {
-  static_assert(R == 8 && R >= 2 * Op::HV + 1, "chunk rows (the ops' window rotation assumes 8-row chunks)");
+  static_assert((R == 8 || R == 16) && R >= 2 * Op::HV + 1,
+                "chunk rows: 8 (the ops' window rotation assumes it) or 16 for ops with more than 3 halo rows -- the border "
+                "patches read at most one chunk back");
   constexpr int HL = OpHaloLanes<Op>::value;
   constexpr int kHalo = HL * kLaneBytes, kOut = kTileBytes - 2 * kHalo;  // halo bytes per side, output bytes per tile row
   static_assert(Op::E * Op::P <= kHalo && (OpHaloLanes<Op>::declared || Op::E * (Op::P + 1) <= 16),
@@ -393,13 +396,13 @@ static inline int pick_band_rows(Ctx *c, const char *optname, int rows, int stri
   return br;
 }
 
-template <class Op, int S = kS, int NW = kNW>
+template <class Op, int S = kS, int NW = kNW, int R = kR>
 static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout, const char *band_opt,
                         cudaStream_t s, const int32_t *taps_x = nullptr, const int32_t *taps_y = nullptr,
-                        const float *ftaps = nullptr, int nftaps = 0) {
+                        const float *ftaps = nullptr, int nftaps = 0, bool wide_taps = false) {
   const CUtensorMap *tmap = nullptr;  // cached per (base, geometry): the reference API calls once per frame on reused buffers
   RCV_TRY(ctx_tmap_rows_u32(c, &tmap, src.v.data, src.v.row_bytes(), src.v.rows, src.v.step, src.n, src.frame_stride,
-                            kTileBytes / 4, kR));
+                            kTileBytes / 4, R));
   StripParams p = {};
   p.vec_store = 1;
   for (int k = 0; k < 3; ++k) {
@@ -431,10 +434,14 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
     p.taps_x[i] = taps_x ? (uint32_t)taps_x[i] : 0;
     p.taps_y[i] = taps_y ? (uint32_t)taps_y[i] : 0;
   }
+  for (int i = 0; i < 8; ++i) {  // wide_taps: the caller's arrays hold 8 entries each
+    p.wtaps[i] = (wide_taps && taps_x) ? (uint32_t)taps_x[i] : 0;
+    p.wtaps[8 + i] = (wide_taps && taps_y) ? (uint32_t)taps_y[i] : 0;
+  }
   for (int i = 0; i < 52; ++i) p.ftaps[i] = (ftaps && i < nftaps) ? ftaps[i] : 0.0f;
 
-  auto kern = k_strip<Op, kR, S, NW>;
-  const int smem = NW * S * kR * kTileBytes + NW * S * 8;
+  auto kern = k_strip<Op, R, S, NW>;
+  const int smem = NW * S * R * kTileBytes + NW * S * 8;
   static bool attr_done[16] = {};  // per template instantiation, per device
   const int dev = ctx_device(c) & 15;
   if (!attr_done[dev]) {

@@ -78,7 +78,12 @@ run("GaussianBlur 5x5 sigma 0, 4K BGR u8 x32 [k_strip<Gauss5Op<3>>]", lambda: I.
 run("GaussianBlur 3x3 sigma 0, 4K BGR u8 x32 [k_strip<Gauss3Op<3>>]", lambda: I.gaussian_blur_batch(bgr, out3, (3, 3), 0.0, 0.0), 6 * PX)
 for ks, sg in ((3, 0.8), (5, 1.0), (7, 1.5)):
     run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32 [k_strip<GaussQ8Op<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
-run("GaussianBlur 11x11 sigma 2, 4K BGR u8 x32 [k_sepfilter<u8,11>]", lambda: I.gaussian_blur_batch(bgr, out3, (11, 11), 2.0, 2.0), 6 * PX)
+for ks, sg in ((9, 1.5), (11, 2.0), (13, 2.0), (15, 2.5)):
+    run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32 [k_strip<GaussQ8WideOp<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
+I.set_option("gauss.no_wide", 1)
+run("GaussianBlur 11x11 sigma 2, 4K BGR u8 x32, general kernel [k_sepfilter<u8,11>]", lambda: I.gaussian_blur_batch(bgr, out3, (11, 11), 2.0, 2.0), 6 * PX)
+I.set_option("gauss.no_wide", 0)
+run("GaussianBlur 17x17 sigma 3, 4K BGR u8 x32, general kernel [k_sepfilter<u8,0>]", lambda: I.gaussian_blur_batch(bgr, out3, (17, 17), 3.0, 3.0), 6 * PX)
 g1 = R.Mat.device_batch(N, H, W, 1)
 x4 = R.Mat.device_batch(N, H, W, 4)
 run("cvtColor BGR->Gray, 4K x32 [k_px16_vec]", lambda: I.cvt_color_batch(bgr, g1, I.COLOR_BGR2GRAY), 4 * PX)

@@ -151,3 +151,50 @@ def test_f32_multichannel_strip_kernels(rcv, oracle, cn, ks):
     hd = R.Mat.pinned(700, 900, cn, R.F32)
     R.imgproc.sep_filter2d(hp, hd, kx, kx)
     assert (hd.to_numpy().view(np.int32) == oracle.sepfilter_f32(big, kx, kx).view(np.int32)).all(), "pinned host, banded"
+
+
+# ---- wide u8 Gaussians in the strip pipeline (strip_gaussq8_wide.cuh): 9..15 taps, 16-row chunks, 8 warps per CTA -------
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("ks", [9, 11, 13, 15])
+def test_gaussian_wide_strip_kernel(rcv, oracle, cn, ks):
+    R = rcv
+    for (h, w) in ((203, 517), (16, 16), (40, 700), (130, 161)):
+        a = oracle.fill_u8(4000 + ks + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+        s = R.Mat.from_numpy(a).upload()
+        d = s.like()
+        for sx, sy in ((0.0, 0.0), (2.0, 2.0), (1.1, 3.7)):
+            n0 = R.imgproc.launch_count()
+            R.imgproc.gaussian_blur(s, d, (ks, ks), sx, sy)
+            assert R.imgproc.launch_count() - n0 == 1
+            want = oracle.gaussian_blur(a, (ks, ks), sx, sy)
+            got = d.to_numpy()
+            assert (got == want).all(), (f"cn{cn} ks{ks} {h}x{w} sigma {sx},{sy}: {(got != want).sum()} differ, first at "
+                                         f"{np.argwhere(got != want)[:3].tolist()}")
+    # band seams, saturated regions, a batch in one launch, host Mats (banded pinned pipeline: row windows)
+    h, w = 300, 420
+    a = oracle.fill_u8(4100 + ks + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+    a[40:90, 100:300] = 255
+    a[200:240, :64] = 0
+    want = oracle.gaussian_blur(a, (ks, ks), 2.5, 2.5)
+    s = R.Mat.from_numpy(a).upload()
+    for br in (8, 24, 50):
+        R.imgproc.set_option("gauss.band_rows", br)
+        d = s.like()
+        R.imgproc.gaussian_blur(s, d, (ks, ks), 2.5)
+        assert (d.to_numpy() == want).all(), f"band_rows {br}"
+    R.imgproc.set_option("gauss.band_rows", 0)
+    big = oracle.fill_u8(4200 + cn, 1200 * 1000 * cn).reshape((1200, 1000) if cn == 1 else (1200, 1000, cn))
+    hp = R.Mat.pinned(1200, 1000, cn)
+    hp.data[:] = big.ravel()
+    hd = R.Mat.pinned(1200, 1000, cn)
+    R.imgproc.gaussian_blur(hp, hd, (ks, ks), 2.0)
+    assert (hd.to_numpy() == oracle.gaussian_blur(big, (ks, ks), 2.0, 2.0)).all(), "pinned host Mat (banded)"
+
+
+def test_gaussian_wide_falls_back_for_tiny_or_two_channel_images(rcv, oracle):
+    R = rcv
+    for shape in ((9, 40, 3), (40, 9, 3), (64, 64, 2)):
+        a = oracle.fill_u8(4300, int(np.prod(shape))).reshape(shape)
+        d = R.Mat.empty()
+        R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, (11, 11), 2.0)
+        assert (d.to_numpy() == oracle.gaussian_blur(a, (11, 11), 2.0, 2.0)).all(), shape
