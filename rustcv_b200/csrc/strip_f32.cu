@@ -166,10 +166,13 @@ int launch_sepf32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const fl
                           cudaStream_t s);
 int launch_filter2d_f32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
                                 cudaStream_t s);
+int launch_sepf32wide_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
+                            cudaStream_t s);
 
 // separable f32, kw == kh in {3, 5, 7}: single channel here, 2..4 channels in strip_f32cn.cu; RCV_ERR_UNSUPPORTED otherwise
 int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
                         cudaStream_t s) {
+  if (kw == kh && kw >= 9) return launch_sepf32wide_strip(c, src, dst, kx, kw, ky, kh, s);  // 9..15 taps, gray / BGR
   if (src.v.cn > 1) return launch_sepf32cn_strip(c, src, dst, kx, kw, ky, kh, s);
   if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
   float taps[14];

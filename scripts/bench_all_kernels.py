@@ -126,12 +126,18 @@ fo = R.Mat.device_batch(NF, FH, FW, 1, R.F32)
 run("Sobel 3x3 + magnitude, 1080p f32 x128 [k_strip<Sobel3Op<0>>]", lambda: I.sobel_mag_batch(f, fo), 8 * NF * FH * FW)
 for ks in (3, 5, 7):
     run(f"GaussianBlur {ks}x{ks} sigma 1.2, 1080p gray f32 x128 [k_strip<SepF32Op<{ks}>>]", lambda: I.gaussian_blur_batch(f, fo, (ks, ks), 1.2, 1.2), 8 * NF * FH * FW)
+for ks, sg in ((9, 1.0), (11, 1.3), (15, 1.8)):
+    run(f"GaussianBlur {ks}x{ks} sigma {sg}, 1080p gray f32 x128 [k_strip<SepF32WideOp<{ks},1>>]", lambda: I.gaussian_blur_batch(f, fo, (ks, ks), sg, sg), 8 * NF * FH * FW)
 f.free(); fo.free()
 f3 = batch(32, FH, FW, 3, R.F32, seed=3)
 fo3 = R.Mat.device_batch(32, FH, FW, 3, R.F32)
 for ks in (3, 5, 7):
     run(f"GaussianBlur {ks}x{ks} sigma 1.2, 1080p BGR f32 x32 [k_strip<SepF32CnOp<{ks},3>>]", lambda: I.gaussian_blur_batch(f3, fo3, (ks, ks), 1.2, 1.2), 24 * 32 * FH * FW)
-run("GaussianBlur 11x11 sigma 2, 1080p BGR f32 x32 [k_sepfilter<f32,11>]", lambda: I.gaussian_blur_batch(f3, fo3, (11, 11), 2.0, 2.0), 24 * 32 * FH * FW)
+for ks, sg in ((9, 1.0), (11, 1.3), (15, 1.8)):
+    run(f"GaussianBlur {ks}x{ks} sigma {sg}, 1080p BGR f32 x32 [k_strip<SepF32WideOp<{ks},3>>]", lambda: I.gaussian_blur_batch(f3, fo3, (ks, ks), sg, sg), 24 * 32 * FH * FW)
+I.set_option("sepf32.no_wide", 1)
+run("GaussianBlur 11x11 sigma 2, 1080p BGR f32 x32, general kernel [k_sepfilter<f32,11>]", lambda: I.gaussian_blur_batch(f3, fo3, (11, 11), 2.0, 2.0), 24 * 32 * FH * FW)
+I.set_option("sepf32.no_wide", 0)
 
 
 def f2df(k):

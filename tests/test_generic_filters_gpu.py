@@ -198,3 +198,42 @@ def test_gaussian_wide_falls_back_for_tiny_or_two_channel_images(rcv, oracle):
         d = R.Mat.empty()
         R.imgproc.gaussian_blur(R.Mat.from_numpy(a), d, (11, 11), 2.0)
         assert (d.to_numpy() == oracle.gaussian_blur(a, (11, 11), 2.0, 2.0)).all(), shape
+
+
+@pytest.mark.parametrize("cn", [1, 3])
+@pytest.mark.parametrize("ks", [9, 11, 13, 15])
+def test_f32_wide_strip_kernel(rcv, oracle, cn, ks):
+    """k_strip<SepF32WideOp<KS,CN>>: 9..15 taps on gray / BGR f32 (16-row chunks, up to 6 halo lanes per side):
+    0 ULP vs the oracle on several strips, ragged edges, borders, band seams, pinned host Mats."""
+    R = rcv
+    rng = np.random.default_rng(ks * 7 + cn)
+    for (h, w) in ((203, 517), (16, 32), (40, 300)):
+        a = oracle.fill_f32(5000 + ks + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+        s = R.Mat.from_numpy(a).upload()
+        d = s.like()
+        kx = rng.normal(size=ks).astype(np.float32)
+        ky = rng.normal(size=ks).astype(np.float32)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.sep_filter2d(s, d, kx, ky)
+        assert R.imgproc.launch_count() - n0 == 1
+        want = oracle.sepfilter_f32(a, kx, ky)
+        assert (d.to_numpy().view(np.int32) == want.view(np.int32)).all(), f"sep cn{cn} ks{ks} {h}x{w}"
+        R.imgproc.gaussian_blur(s, d, (ks, ks), 2.1)
+        wg = oracle.gaussian_blur(a, (ks, ks), 2.1, 2.1)
+        assert (d.to_numpy().view(np.int32) == wg.view(np.int32)).all(), f"gauss cn{cn} ks{ks} {h}x{w}"
+    a = oracle.fill_f32(5100 + ks + cn, 150 * 300 * cn).reshape((150, 300) if cn == 1 else (150, 300, cn))
+    s = R.Mat.from_numpy(a).upload()
+    kx = rng.normal(size=ks).astype(np.float32)
+    want = oracle.sepfilter_f32(a, kx, kx)
+    for br in (8, 30, 50):
+        R.imgproc.set_option("sepf32.band_rows", br)
+        d = s.like()
+        R.imgproc.sep_filter2d(s, d, kx, kx)
+        assert (d.to_numpy().view(np.int32) == want.view(np.int32)).all(), f"band_rows {br}"
+    R.imgproc.set_option("sepf32.band_rows", 0)
+    big = oracle.fill_f32(5200 + cn, 700 * 900 * cn).reshape((700, 900) if cn == 1 else (700, 900, cn))
+    hp = R.Mat.pinned(700, 900, cn, R.F32)
+    hp.data[:] = big.view(np.uint8).ravel()
+    hd = R.Mat.pinned(700, 900, cn, R.F32)
+    R.imgproc.sep_filter2d(hp, hd, kx, kx)
+    assert (hd.to_numpy().view(np.int32) == oracle.sepfilter_f32(big, kx, kx).view(np.int32)).all(), "pinned host, banded"
