@@ -90,8 +90,8 @@ static int launch_sepf32wide_ks(Ctx *c, const DBatch &src, const DBatch &dst, co
   // gray: under 170 registers per thread, so 12 warps fit (2 stages of 16 rows per warp = 192 KB per CTA)
   if (src.v.cn == 1) return launch_strip<SepF32WideOp<KS, 1>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
   if (src.v.cn == 3) {
-    if (KS <= 9) return launch_strip<SepF32WideOp<KS, 3>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
-    return launch_strip<SepF32WideOp<KS, 3>, kS, 8, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
+    if constexpr (KS <= 9) return launch_strip<SepF32WideOp<KS, 3>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
+    else return launch_strip<SepF32WideOp<KS, 3>, kS, 8, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
   }
   return RCV_ERR_UNSUPPORTED;
 }
