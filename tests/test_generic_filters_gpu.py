@@ -237,3 +237,58 @@ def test_f32_wide_strip_kernel(rcv, oracle, cn, ks):
     hd = R.Mat.pinned(700, 900, cn, R.F32)
     R.imgproc.sep_filter2d(hp, hd, kx, kx)
     assert (hd.to_numpy().view(np.int32) == oracle.sepfilter_f32(big, kx, kx).view(np.int32)).all(), "pinned host, banded"
+
+
+def test_round2_strip_ops_random_geometries(rcv, oracle):
+    """40 random (rows, cols, channels, taps, band height, location) draws over the strip ops added in round 2 --
+    multi-channel f32 (3 / 5 / 7 taps), wide u8 and wide f32 (9..15 taps): every ragged-edge / band-seam / partial-chunk
+    / halo-lane combination they can meet, against the oracle (bit-exact / 0 ULP)."""
+    R = rcv
+    rng = np.random.default_rng(20261019)
+
+    def place(a, where):
+        if where == "host":
+            return R.Mat.from_numpy(a), R.Mat.empty()
+        s = R.Mat.from_numpy(a).upload()
+        return s, s.like()
+
+    for it in range(40):
+        h = int(rng.integers(16, 300))
+        w = int(rng.integers(32, 700))
+        band = int(rng.choice([0, 8, 12, 24, 40, 98]))
+        where = str(rng.choice(["device", "host"]))
+        R.imgproc.set_option("gauss.band_rows", band)
+        R.imgproc.set_option("sepf32.band_rows", band)
+        try:
+            # wide u8 Gaussian
+            cn = int(rng.choice([1, 3, 4]))
+            ks = int(rng.choice([9, 11, 13, 15]))
+            sx, sy = float(rng.uniform(0.8, 4.0)), float(rng.uniform(0.8, 4.0))
+            a = rng.integers(0, 256, size=(h, w, cn), dtype=np.uint8)
+            if cn == 1:
+                a = a.reshape(h, w)
+            s, d = place(a, where)
+            R.imgproc.gaussian_blur(s, d, (ks, ks), sx, sy)
+            assert (d.to_numpy() == oracle.gaussian_blur(a, (ks, ks), sx, sy)).all(), f"wide u8 it{it} {h}x{w}x{cn} ks{ks} band{band} {where}"
+            # multi-channel f32, 3 / 5 / 7 taps
+            cn = int(rng.integers(2, 5))
+            ks = int(rng.choice([3, 5, 7]))
+            f = rng.random(size=(h, w, cn), dtype=np.float32)
+            kx = rng.normal(size=ks).astype(np.float32)
+            ky = rng.normal(size=ks).astype(np.float32)
+            s, d = place(f, where)
+            R.imgproc.sep_filter2d(s, d, kx, ky)
+            assert (d.to_numpy().view(np.int32) == oracle.sepfilter_f32(f, kx, ky).view(np.int32)).all(), f"f32 cn it{it} {h}x{w}x{cn} ks{ks} band{band} {where}"
+            # wide f32, gray / BGR
+            cn = int(rng.choice([1, 3]))
+            ks = int(rng.choice([9, 11, 13, 15]))
+            f = rng.random(size=(h, w, cn), dtype=np.float32)
+            if cn == 1:
+                f = f.reshape(h, w)
+            kx = rng.normal(size=ks).astype(np.float32)
+            s, d = place(f, where)
+            R.imgproc.sep_filter2d(s, d, kx, kx)
+            assert (d.to_numpy().view(np.int32) == oracle.sepfilter_f32(f, kx, kx).view(np.int32)).all(), f"wide f32 it{it} {h}x{w}x{cn} ks{ks} band{band} {where}"
+        finally:
+            R.imgproc.set_option("gauss.band_rows", 0)
+            R.imgproc.set_option("sepf32.band_rows", 0)
