@@ -14,50 +14,49 @@ struct Gauss5Op {
   static constexpr int P = 2;    // pixels of horizontal halo
   static constexpr int E = CN;   // bytes per pixel
   static constexpr int NOUT = 1;
-  static constexpr int UNROLL = 8;  // rows unrolled in the hot loop (window period 4; 8 measured faster: 8.05 vs 8.55 us)
-  uint32_t win[4][8];  // last 4 rows, unpacked: [2w] = bytes 0,2 of word w; [2w+1] = bytes 1,3
+  static constexpr int UNROLL = 8;       // rows unrolled in the hot loop: the whole chunk (8.05 vs 8.55 us per 4K frame at 4)
+  static constexpr int UNROLL_SLOW = 2;  // the per-row-tested loop (ragged strips, a band's last partial chunk) stays small
+  static constexpr bool HOIST_WARM = true;
+  // Vertical pass in transposed form: instead of the last four rows, the partial sums they have contributed to the
+  // next four outputs.  After row x_n:  s4 = x_n,  s3 = x_{n-1} + 4 x_n,  s2 = x_{n-2} + 4 x_{n-1} + 6 x_n,
+  // s1 = x_{n-3} + 4 x_{n-2} + 6 x_{n-1} + 4 x_n.  Row x_{n+1} completes V = s1 + x_{n+1} and moves every sum up one
+  // slot with one multiply-add each: four operations per register pair like the windowed form, but every state
+  // register is rewritten in place, row after row -- no rotating window, so ptxas needs no moves at the loop's
+  // back edge (the windowed form carried 8 per row) and the loops may be unrolled by any count.
+  uint32_t s1[8], s2[8], s3[8], s4[8];
 
   __device__ __forceinline__ void init(const StripParams &) {}
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) win[j][h] = 0;
-  }
+  __device__ __forceinline__ void reset() {}  // four warm-up rows overwrite every state register
 
-  // The first 2*HV rows of a band only fill the window.
+  // The first 2*HV rows of a band only build the sums: row J8 (0..3) of the band needs J8 operations per pair.
   template <int J8>
   __device__ __forceinline__ void warm(const uint4 &q) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      win[J8 & 3][2 * k] = __byte_perm(w[k], 0, 0x4240);
-      win[J8 & 3][2 * k + 1] = __byte_perm(w[k], 0, 0x4341);
+    for (int h = 0; h < 8; ++h) {
+      const uint32_t x = __byte_perm(w[h >> 1], 0, (h & 1) ? 0x4341 : 0x4240);
+      if (J8 >= 3) s1[h] = madc<4>(x, s2[h]);
+      if (J8 >= 2) s2[h] = madc<6>(x, s3[h]);
+      if (J8 >= 1) s3[h] = madc<4>(x, s4[h]);
+      s4[h] = x;
     }
   }
 
-  // J = (feed index) & 3, compile time: win[J] holds the oldest row.
-  // FAST: interior rows of an aligned, non-ragged strip -- always emits, lanes store 16 B or nothing.
+  // FAST: interior rows of an aligned, full-width strip -- always emits, lanes store 16 B or nothing.
   template <int J8, bool FAST>
   __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    constexpr int J = J8 & 3;
-    uint32_t in[8];
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      in[2 * k] = __byte_perm(w[k], 0, 0x4240);      // (b0, b2) as 16-bit lanes
-      in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);  // (b1, b3)
-    }
     // vertical: V = r0 + 4 r1 + 6 r2 + 4 r3 + r4 (+8 per lane: with horizontal taps summing
     // to 16 that is the final "+128" rounding term).  V <= 4088 per 16-bit lane.
     uint32_t V[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
-      const uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
-      const uint32_t a = add3(r0, in[h], 0x00080008u);
-      const uint32_t b = add2(r1, r3);
-      V[h] = madc<6>(r2, madc<4>(b, a));
-      win[J][h] = in[h];
+      const uint32_t x = __byte_perm(w[h >> 1], 0, (h & 1) ? 0x4341 : 0x4240);  // (b0, b2) / (b1, b3) as 16-bit lanes
+      V[h] = add3(s1[h], x, 0x00080008u);
+      s1[h] = madc<4>(x, s2[h]);
+      s2[h] = madc<6>(x, s3[h]);
+      s3[h] = madc<4>(x, s4[h]);
+      s4[h] = x;
     }
     if (!FAST && !emit) return;
 

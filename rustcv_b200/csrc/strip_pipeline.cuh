@@ -59,6 +59,8 @@ struct StripParams {
   int n_frames;
   int vec_store;  // all outputs 16-byte aligned (base, step, frame stride)
   long long total_items;
+  uint32_t div_strips_mul, div_strips_sh;  // item / strips == umulhi(item, mul) >> sh for every item of this launch (mul = 0: divide)
+  uint32_t div_bands_mul, div_bands_sh;
   unsigned long long *next_item;  // dynamic scheduler: items beyond the first round (NULL = static stride)
   unsigned long long *reset_item; // the OTHER counter of the pair: zeroed here for the next launch on this stream
   uint32_t taps_x[4], taps_y[4];  // GaussQ8Op: symmetric Q8 taps, [0] outermost .. [KS/2] centre
@@ -96,6 +98,11 @@ __device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
 //   Op::BAND_ROWS  output rows per work item when the job is large (default 40 - 2*HV);
 //   Op::EDGES the op applies the horizontal border itself (on its vertical sums, in registers) and is told
 //             per item where the row's edges are: op.edges(left_edge, right_edge, xr, lane);
+//   Op::HOIST_WARM  the first chunk of a band (2*HV window-filling rows, then R - 2*HV emitting rows) gets its own
+//             straight-line copy of the row bodies, so the steady-state loop carries no warm-up tests (ops whose row
+//             body is short enough that the second copy still fits the instruction cache);
+//   Op::UNROLL_SLOW  rows unrolled in the per-row-tested loop (default UNROLL): ops without a rotating register
+//             window can keep that rarely used loop small;
 //   Op::MACRO horizontal border elements are macro-pixels reflected INCLUDING the edge element
 //             (element -1 <- element 0, element n <- element n-1) instead of REFLECT_101.
 //   Op::HALO_LANES  halo lanes per side (default 1): an op whose horizontal reach P*E exceeds 16 bytes (multi-channel
@@ -130,6 +137,14 @@ struct OpHaloLanes<Op, std::void_t<decltype(Op::HALO_LANES)>> {
   static constexpr int value = Op::HALO_LANES;
   static constexpr bool declared = true;
 };
+template <class Op, class = void>
+struct OpHoistWarm { static constexpr bool value = false; };
+template <class Op>
+struct OpHoistWarm<Op, std::void_t<decltype(Op::HOIST_WARM)>> { static constexpr bool value = Op::HOIST_WARM; };
+template <class Op, class = void>
+struct OpUnrollSlow { static constexpr int value = Op::UNROLL; };
+template <class Op>
+struct OpUnrollSlow<Op, std::void_t<decltype(Op::UNROLL_SLOW)>> { static constexpr int value = Op::UNROLL_SLOW; };
 template <class Op, class = void>
 struct OpMacro { static constexpr int value = 0; };
 template <class Op>
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_item != nullptr) *p.reset_item = 0ULL;
 
   uint32_t phase = 0;  // bit s = parity the next wait on stage s must see
+  bool dirty = false;  // lane 0: generic-proxy writes (border patches) may be pending in the ring
   const long long total_warps = (long long)gridDim.x * NW;
   Op op;
   op.init(p);
@@ -184,13 +200,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     // claim the next item now; the atomic's latency hides behind this item's work
     unsigned long long claimed = 0;
     if (p.next_item != nullptr && lane == 0) claimed = atomicAdd(p.next_item, 1ULL);
-    // 32-bit item arithmetic (the launcher refuses jobs of 2^31 items): the 64-bit divisions were ~300
-    // instructions per item, 6 % of a 36-row band of the 5x5 Gaussian
+    // 32-bit item arithmetic (the launcher refuses jobs of 2^31 items) with host-made reciprocals: the 64-bit
+    // divisions were ~300 instructions per item (6 % of a 36-row band of the 5x5 Gaussian), 32-bit ones ~50
     const unsigned it32 = (unsigned)item;
-    const int strip = (int)(it32 % (unsigned)p.strips);
-    const unsigned t = it32 / (unsigned)p.strips;
-    const int band = (int)(t % (unsigned)p.bands);
-    const int frame = (int)(t / (unsigned)p.bands);
+    const unsigned t = p.div_strips_mul ? (__umulhi(it32, p.div_strips_mul) >> p.div_strips_sh) : it32 / (unsigned)p.strips;
+    const int strip = (int)(it32 - t * (unsigned)p.strips);
+    const unsigned fr = p.div_bands_mul ? (__umulhi(t, p.div_bands_mul) >> p.div_bands_sh) : t / (unsigned)p.bands;
+    const int band = (int)(t - fr * (unsigned)p.bands);
+    const int frame = (int)fr;
     const int x0 = strip * kOut;
     const int y0 = p.row_begin + band * p.band_rows;
     const int y1 = min(y0 + p.band_rows, p.row_end);
@@ -203,7 +220,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
     const int xr = kHalo + (p.row_bytes - x0);  // tile byte offset of the first byte past the row
     const bool top = (ys < 0);
     const bool bottom = (y1 + HV > p.rows);  // the fed rows run past the last image row
-    const bool fast_strip = p.vec_store != 0 && !right_edge;  // full 16-byte stores in lanes 1..30
+    const bool edgy = left_edge || right_edge || top || bottom;  // some chunk of this item gets patched
+    // full 16-byte stores in every output lane: aligned outputs and a strip that is not cut by the row's end
+    const bool fast_strip = p.vec_store != 0 && p.row_bytes >= x0 + kOut;
 
     // this lane's slice of the outputs
     const int xl = x0 + (lane - HL) * kLaneBytes;
@@ -217,94 +236,136 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
                     ? p.out[k].data + (size_t)frame * p.out[k].fs + (size_t)y0 * p.out[k].step + (long long)xl * OM / OD
                     : nullptr;
 
-    auto issue = [&](int c) {
-      const uint32_t st = (uint32_t)(c % S);
-      fence_proxy_async();
+    // Lane 0 only.  The proxy fence orders the border patches' generic-proxy writes before the TMA write that
+    // recycles the stage; interior items never write the ring (their reads are complete -- consumed -- before the
+    // __syncwarp that precedes every refill), so they skip it.
+    auto issue = [&](int c, uint32_t st) {
+      if (dirty) fence_proxy_async();
       mbar_expect_tx(bars + st * 8, kStageBytes);
       tma_load_3d(tiles + st * kStageBytes, &tmap, bars + st * 8, cx, ys + c * R, frame);
     };
 
     if (lane == 0) {
-      for (int c = 0; c < S && c < n_chunks; ++c) issue(c);
+      dirty = dirty || edgy;  // the previous item's patches, or (from chunk 1 on) this item's
+      for (int c = 0; c < S && c < n_chunks; ++c) issue(c, (uint32_t)c);
+      dirty = edgy;
     }
     op.reset();
     if constexpr (OpEdges<Op>::value) op.edges(left_edge, right_edge, xr, lane);
 
+    uint32_t st = 0;  // stage of chunk c = c % S, kept incrementally
     for (int c = 0; c < n_chunks; ++c) {
-      const uint32_t st = (uint32_t)(c % S);
       const uint32_t tile = tiles + st * kStageBytes;
       mbar_wait(bars + st * 8, (phase >> st) & 1u);
       phase ^= 1u << st;
+      const uint32_t st_prev = st == 0 ? (uint32_t)(S - 1) : st - 1;  // stage of chunk c-1 == stage of chunk c-1+S
+      st = st + 1 == (uint32_t)S ? 0u : st + 1;
 
       // ---- BORDER_REFLECT_101 patches (edge strips / bands only; warp-uniform branches) ----
-      if (left_edge || right_edge) {
-        if (lane < R) {
-          const uint32_t row = tile + lane * kTileBytes;
-          if (left_edge) {
+      if (edgy) {
+        if (left_edge || right_edge) {
+          if (lane < R) {
+            const uint32_t row = tile + lane * kTileBytes;
+            if (left_edge) {
 #pragma unroll
-            for (int k = 1; k <= P; ++k)
+              for (int k = 1; k <= P; ++k)
 #pragma unroll
-              for (int b = 0; b < E; ++b) sts8(row + kHalo - k * E + b, lds8(row + kHalo + (k - RO) * E + b));
+                for (int b = 0; b < E; ++b) sts8(row + kHalo - k * E + b, lds8(row + kHalo + (k - RO) * E + b));
+            }
+            if (right_edge) {
+#pragma unroll
+              for (int k = 1; k <= P; ++k)
+#pragma unroll
+                for (int b = 0; b < E; ++b) {
+                  const int dsto = xr + (k - 1) * E + b;
+                  if (dsto < kTileBytes) sts8(row + dsto, lds8(row + xr - (k + 1 - RO) * E + b));
+                }
+            }
           }
-          if (right_edge) {
-#pragma unroll
-            for (int k = 1; k <= P; ++k)
-#pragma unroll
-              for (int b = 0; b < E; ++b) {
-                const int dsto = xr + (k - 1) * E + b;
-                if (dsto < kTileBytes) sts8(row + dsto, lds8(row + xr - (k + 1 - RO) * E + b));
-              }
-          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      if (top && c == 0) {
-        // global row -k (slot HV-k) <- row k (slot HV+k)
+        if (top && c == 0) {
+          // global row -k (slot HV-k) <- row k (slot HV+k)
 #pragma unroll
-        for (int k = 1; k <= HV; ++k)
-          sts128(tile + (HV - k) * kTileBytes + lane * kLaneBytes, lds128(tile + (HV + k) * kTileBytes + lane * kLaneBytes));
-      }
-      if (bottom) {
-        // global row rows-1+k <- row rows-1-k; the source is in this chunk or the previous one
+          for (int k = 1; k <= HV; ++k)
+            sts128(tile + (HV - k) * kTileBytes + lane * kLaneBytes, lds128(tile + (HV + k) * kTileBytes + lane * kLaneBytes));
+        }
+        if (bottom) {
+          // global row rows-1+k <- row rows-1-k; the source is in this chunk or the previous one
 #pragma unroll
-        for (int k = 1; k <= HV; ++k) {
-          const int fi = p.rows - 1 + k - ys;  // feed index of the reflected row
-          if (fi / R == c) {
-            const int fs_ = fi - 2 * k;
-            const uint32_t src_tile = tiles + (uint32_t)((fs_ / R) % S) * kStageBytes;
-            sts128(tile + (fi % R) * kTileBytes + lane * kLaneBytes,
-                   lds128(src_tile + (fs_ % R) * kTileBytes + lane * kLaneBytes));
+          for (int k = 1; k <= HV; ++k) {
+            const int fi = p.rows - 1 + k - ys;  // feed index of the reflected row
+            if (fi / R == c) {
+              const int fs_ = fi - 2 * k;
+              const uint32_t src_tile = tiles + (uint32_t)((fs_ / R) % S) * kStageBytes;
+              sts128(tile + (fi % R) * kTileBytes + lane * kLaneBytes,
+                     lds128(src_tile + (fs_ % R) * kTileBytes + lane * kLaneBytes));
+            }
           }
         }
       }
       __syncwarp();
       // every lane is past chunk c-1: refill its stage
-      if (lane == 0 && c >= 1 && c - 1 + S < n_chunks) issue(c - 1 + S);
+      if (lane == 0 && c >= 1 && c - 1 + S < n_chunks) issue(c - 1 + S, st_prev);
 
       // ---- rows of this chunk ----
       if (!OpSinglePath<Op>::value && fast_strip && c * R + R <= n_feed) {
-        // whole chunk of an aligned, non-ragged strip: every row is fed; every row emits except the
+        // whole chunk of an aligned, full-width strip: every row is fed; every row emits except the
         // first 2*HV rows of the band (chunk 0), which only fill the window.  No per-row tests.
         // The body is unrolled Op::UNROLL rows (the op's window period) and looped R/UNROLL times:
         // unrolling all 8 rows of the wider ops would not fit the 32 KB instruction cache.
         constexpr int U = Op::UNROLL;
         static_assert(R % U == 0, "window period must divide the chunk");
+        if constexpr (OpHoistWarm<Op>::value) {
+          if (c == 0) {  // the band's first chunk, straight-line: 2*HV rows fill the window, the rest emit
+            const uint32_t rowaddr = tile + lane * kLaneBytes;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const uint4 q = lds128(rowaddr + j * kTileBytes);
+              if (j < 2 * HV) {
+                if (j == 0) op.template warm<0>(q);
+                if (j == 1) op.template warm<1>(q);
+                if (j == 2) op.template warm<2>(q);
+                if (j == 3) op.template warm<3>(q);
+                if (j == 4) op.template warm<4>(q);
+                if (j == 5) op.template warm<5>(q);
+                if (j == 6) op.template warm<6>(q);
+                if (j == 7) op.template warm<7>(q);
+              } else {
+                if (j == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
+                if (j == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
+                if (j == 2) op.template feed<2, true>(q, true, optr, nvalid, true);
+                if (j == 3) op.template feed<3, true>(q, true, optr, nvalid, true);
+                if (j == 4) op.template feed<4, true>(q, true, optr, nvalid, true);
+                if (j == 5) op.template feed<5, true>(q, true, optr, nvalid, true);
+                if (j == 6) op.template feed<6, true>(q, true, optr, nvalid, true);
+                if (j == 7) op.template feed<7, true>(q, true, optr, nvalid, true);
+#pragma unroll
+                for (int k = 0; k < Op::NOUT; ++k)
+                  if (Op::NOUT == 1 || optr[k]) optr[k] += p.out[k].step;
+              }
+            }
+            continue;
+          }
+        }
 #pragma unroll 1
         for (int g = 0; g < R / U; ++g) {
           const uint32_t rowaddr = tile + (uint32_t)(g * U) * kTileBytes + lane * kLaneBytes;
 #pragma unroll
           for (int j = 0; j < U; ++j) {
             const uint4 q = lds128(rowaddr + j * kTileBytes);
-            if (c == 0 && g * U + j < 2 * HV) {
-              if (j == 0) op.template warm<0>(q);
-              if (j == 1) op.template warm<1>(q);
-              if (j == 2) op.template warm<2>(q);
-              if (j == 3) op.template warm<3>(q);
-              if (j == 4) op.template warm<4>(q);
-              if (j == 5) op.template warm<5>(q);
-              if (j == 6) op.template warm<6>(q);
-              if (j == 7) op.template warm<7>(q);
-              continue;
+            if constexpr (!OpHoistWarm<Op>::value) {
+              if (c == 0 && g * U + j < 2 * HV) {
+                if (j == 0) op.template warm<0>(q);
+                if (j == 1) op.template warm<1>(q);
+                if (j == 2) op.template warm<2>(q);
+                if (j == 3) op.template warm<3>(q);
+                if (j == 4) op.template warm<4>(q);
+                if (j == 5) op.template warm<5>(q);
+                if (j == 6) op.template warm<6>(q);
+                if (j == 7) op.template warm<7>(q);
+                continue;
+              }
             }
             if (j == 0) op.template feed<0, true>(q, true, optr, nvalid, true);
             if (j == 1) op.template feed<1, true>(q, true, optr, nvalid, true);
@@ -322,13 +383,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
         continue;
       }
       // first / last chunks of a band, ragged or unaligned strips: per-row tests
+      constexpr int US = OpUnrollSlow<Op>::value;
 #pragma unroll 1
-      for (int g = 0; g < R / Op::UNROLL; ++g) {
-        const uint32_t rowaddr = tile + (uint32_t)(g * Op::UNROLL) * kTileBytes + lane * kLaneBytes;
+      for (int g = 0; g < R / US; ++g) {
+        const uint32_t rowaddr = tile + (uint32_t)(g * US) * kTileBytes + lane * kLaneBytes;
         // feed index fi produces output row y0 + fi - 2*HV
 #pragma unroll
-        for (int j = 0; j < Op::UNROLL; ++j) {
-          const int fi = c * R + g * Op::UNROLL + j;
+        for (int j = 0; j < US; ++j) {
+          const int fi = c * R + g * US + j;
           if (fi < n_feed) {
             const uint4 q = lds128(rowaddr + j * kTileBytes);
             const bool emit = fi >= 2 * HV;
@@ -368,6 +430,25 @@ static inline bool aligned16(const DBatch &b) {
 
 static inline bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
   return aligned16(src) && src.v.rows >= min_rows && src.v.cols >= min_cols;
+}
+
+// n / d == umulhi(n, mul) >> sh for every n < n_max (Granlund-Montgomery round-up reciprocal, checked against its error
+// bound here); mul = 0 tells the kernel to divide.
+static inline void strip_fast_div(uint32_t d, uint64_t n_max, uint32_t *mul, uint32_t *sh) {
+  *mul = 0;
+  *sh = 0;
+  if (d < 2) return;
+  for (uint32_t s = 0; s < 32; ++s) {
+    const unsigned __int128 two = (unsigned __int128)1 << (32 + s);
+    const unsigned __int128 m = (two + d - 1) / d;  // ceil(2^(32+s) / d)
+    if (m >> 32) break;
+    const unsigned __int128 e = m * d - two;        // 0 <= e < d; exact while n * e < 2^(32+s)
+    if ((unsigned __int128)n_max * e < two) {
+      *mul = (uint32_t)m;
+      *sh = s;
+      return;
+    }
+  }
 }
 
 // Picks the band height.  Measured on B200 (profiles/README.md, sweep r1d): short bands win
@@ -428,6 +509,8 @@ static int launch_strip(Ctx *c, const DBatch &src, const DBatch *outs, int nout,
   p.n_frames = src.n;
   p.total_items = (long long)p.strips * p.bands * src.n;
   if (p.total_items >= (1LL << 31)) return RCV_ERR_UNSUPPORTED;  // the kernel decodes items in 32 bits
+  strip_fast_div((uint32_t)p.strips, (uint64_t)p.total_items, &p.div_strips_mul, &p.div_strips_sh);
+  strip_fast_div((uint32_t)p.bands, (uint64_t)p.total_items, &p.div_bands_mul, &p.div_bands_sh);
   p.next_item = nullptr;
   p.reset_item = nullptr;
   for (int i = 0; i < 4; ++i) {
