@@ -651,32 +651,68 @@ def main() -> None:
         sustained = {"steps": n_sus, "seconds": n_sus * sus_ms * 1e-3, "ms_per_step": sus_ms,
                      "value": total_pix / (sus_ms * 1e-3) / 1e6, "achieved": ach, "frac": ach / peak,
                      "clocks": sampler.window(t0 + 0.2, t1) if rank == 0 else None}
-        # context for that number: what a PLAIN COPY (the kernel MEASURED_PEAKS.json's hbm_gbs was taken with, torch
-        # copy_, as a burst) sustains over the same length of time on this GPU, right after -- same power cap, same clocks
+        # context for that number: what a PLAIN COPY (torch copy_, the kernel MEASURED_PEAKS.json's hbm_gbs was taken with)
+        # sustains over the same length of time on this GPU, right after, ON THE SAME PIXELS: the power the memory system
+        # draws depends on how many data lines toggle (profiles/r2_power_vs_content.txt: a copy of zeros stays at 1965 MHz
+        # and ~800 W, a copy of these noise frames sits at the 1 kW cap like our kernel does) -- and then the same step
+        # on all-zero frames, where no cap is reached: what the kernel itself sustains when power is not the limit.
         if rank == 0:
+            def copy_loop(a, b, what):
+                for _ in range(3):
+                    b.copy_(a)
+                torch.cuda.synchronize(dev)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                b.copy_(a)
+                c1.record()
+                torch.cuda.synchronize(dev)
+                n_cp = max(10, int(args.sustained_s * 1e3 / max(c0.elapsed_time(c1), 1e-3)))
+                tc0 = time.time()
+                c0.record()
+                for _ in range(n_cp):
+                    b.copy_(a)
+                c1.record()
+                torch.cuda.synchronize(dev)
+                tc1 = time.time()
+                cp_gbs = 2 * a.numel() * n_cp / (c0.elapsed_time(c1) * 1e-3) / 1e9
+                return {"gbs": cp_gbs, "seconds": c0.elapsed_time(c1) * 1e-3, "frac_of_this": ach / cp_gbs,
+                        "clocks": sampler.window(tc0 + 0.2, tc1), "what": what}
+
             a = torch.empty(F_ * PIX * CN, dtype=torch.uint8, device=dev)
             b = torch.empty_like(a)
-            for _ in range(3):
-                b.copy_(a)
-            torch.cuda.synchronize(dev)
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            b.copy_(a)
-            c1.record()
-            torch.cuda.synchronize(dev)
-            n_cp = max(10, int(args.sustained_s * 1e3 / max(c0.elapsed_time(c1), 1e-3)))
-            tc0 = time.time()
-            c0.record()
-            for _ in range(n_cp):
-                b.copy_(a)
-            c1.record()
-            torch.cuda.synchronize(dev)
-            tc1 = time.time()
-            cp_gbs = 2 * a.numel() * n_cp / (c0.elapsed_time(c1) * 1e-3) / 1e9
-            sustained["plain_copy_sustained"] = {"gbs": cp_gbs, "seconds": c0.elapsed_time(c1) * 1e-3,
-                                                 "frac_of_this": ach / cp_gbs, "clocks": sampler.window(tc0 + 0.2, tc1),
-                                                 "what": "torch b.copy_(a) over the same 2 x 796 MB, looped for the same time"}
+            for i in range(F_):  # the bench's own frames (device -> host -> this tensor; set-up, untimed)
+                a[i * PIX * CN:(i + 1) * PIX * CN].copy_(torch.from_numpy(src[i].to_numpy().reshape(-1)))
+            time.sleep(1.0)
+            sustained["plain_copy_sustained"] = copy_loop(
+                a, b, "torch b.copy_(a) over the same 2 x 796 MB holding the SAME frames (SplitMix64 noise), looped for the same time")
+            a.zero_()
+            time.sleep(1.0)
+            sustained["plain_copy_sustained_zeros"] = copy_loop(a, b, "the same copy over all-zero buffers")
             del a, b
+            # the metric step on all-zero frames (dst is scratch here: parity was checked above, e2e refills its own Mats)
+            zsrc = R.Mat.device_batch(F_, ROWS, COLS, CN)
+            host.data[:] = 0
+            for i in range(F_):
+                F.check(F.lib.rcv_mat_upload(C.byref(host.c()), C.byref(zsrc[i].c())))
+            R.imgproc.sync(local)
+            time.sleep(1.0)
+            for _ in range(5):
+                R.imgproc.sep_filter2d_q8_batch(zsrc, dst, taps, taps)
+            tz0 = time.time()
+            e0.record(stream)
+            for _ in range(n_sus):
+                R.imgproc.sep_filter2d_q8_batch(zsrc, dst, taps, taps)
+            e1.record(stream)
+            R.imgproc.sync(local)
+            tz1 = time.time()
+            z_ms = e0.elapsed_time(e1) / n_sus
+            z_ach = ALGO_BYTES_PER_PIXEL * F_ * PIX / (z_ms * 1e-3) / 1e9
+            sustained["zero_content"] = {"steps": n_sus, "ms_per_step": z_ms, "achieved": z_ach, "frac": z_ach / peak,
+                                         "clocks": sampler.window(tz0 + 0.2, tz1),
+                                         "what": "the same step for the same number of launches on all-zero frames (no data line toggles)"}
+            zsrc.free()
+            step()  # dst holds the blurred noise frames again
+            R.imgproc.sync(local)
         barrier()
 
     # ---- single synchronous call on a device-resident Mat (the reference API's own shape) --------------

@@ -47,19 +47,24 @@ __device__ __forceinline__ Px6 yuv_word(uint32_t w) {
 // the two shifted sums fit signed 16-bit lanes: one PRMT takes bytes 1-2 of both sums (= x >> 8 truncated to 16
 // bits) and one VIMNMX.S16x2.RELU clamps both to [0, 255] -- 2 instructions per channel instead of 2 clamps + a
 // pack.  Exactly clamp((...) >> 8) of the reference formula (floor shift first, then clamp).
+__device__ __forceinline__ uint32_t mad298(int y, int d) {  // 298 * y + d as ONE multiply-add (NVVM would share 298 * y and add three times)
+  int r;
+  asm("mad.lo.s32 %0, %1, 298, %2;" : "=r"(r) : "r"(y), "r"(d));
+  return (uint32_t)r;
+}
+
 template <bool UYVY>
 __device__ __forceinline__ void yuv_word_pairs(uint32_t w, uint32_t &pb, uint32_t &pg, uint32_t &pr) {
   const int y0 = (int)__byte_perm(w, 0, UYVY ? 0x4441 : 0x4440);
   const int u = (int)__byte_perm(w, 0, UYVY ? 0x4440 : 0x4441);
   const int y1 = (int)__byte_perm(w, 0, UYVY ? 0x4443 : 0x4442);
   const int v = (int)__byte_perm(w, 0, UYVY ? 0x4442 : 0x4443);
-  const int cy0 = y0 * 298, cy1 = y1 * 298;
   const int db = u * 516 - 70688;
   const int dr = v * 409 - 56992;
   const int dg = u * -100 + (v * -208 + 34784);
-  pb = __vimin_s16x2_relu(__byte_perm((uint32_t)(cy0 + db), (uint32_t)(cy1 + db), 0x6521), 0x00FF00FFu);
-  pg = __vimin_s16x2_relu(__byte_perm((uint32_t)(cy0 + dg), (uint32_t)(cy1 + dg), 0x6521), 0x00FF00FFu);
-  pr = __vimin_s16x2_relu(__byte_perm((uint32_t)(cy0 + dr), (uint32_t)(cy1 + dr), 0x6521), 0x00FF00FFu);
+  pb = __vimin_s16x2_relu(__byte_perm(mad298(y0, db), mad298(y1, db), 0x6521), 0x00FF00FFu);
+  pg = __vimin_s16x2_relu(__byte_perm(mad298(y0, dg), mad298(y1, dg), 0x6521), 0x00FF00FFu);
+  pr = __vimin_s16x2_relu(__byte_perm(mad298(y0, dr), mad298(y1, dr), 0x6521), 0x00FF00FFu);
 }
 
 }  // namespace rcv

@@ -8,11 +8,15 @@ namespace rcv {
 // ---------------------------------------------------------------------------------------
 // Op: KS x KS Gaussian (KS = 3, 5, 7) on u8 with arbitrary symmetric Q8 taps (any sigma):
 //   out = (sum_i sum_j ky_i kx_j p + 2^15) >> 16      (oracle: orc_sepfilter_u8_q8; == OpenCV)
-// Still two samples per register as 16-bit lanes, exactly:
-//   vertical   V = sum ky_i p <= 255*256 = 65280 fits a lane;
-//   horizontal needs 24 bits, so V is split into bytes Vh = V >> 8, Vl = V & 255 and
-//              A = sum kx_j Vh_j, B = sum kx_j Vl_j (each <= 65280) are accumulated separately;
-//   (256 A + B + 2^15) >> 16 == (A + (B >> 8) + 128) >> 8, and A + (B >> 8) + 128 <= 65408.
+// The sum is exact whatever the order, so the HORIZONTAL pass runs first, on the raw bytes, where two samples per
+// register still work:  H = sum kx_j p <= 255 * 256 = 65280 fits a 16-bit lane (neighbour columns by shuffle,
+// stride-CN taps by PRMT, as in Gauss5Op).  The vertical pass needs 24 bits; it runs on one sample per register,
+// in transposed form: every sample keeps KS-1 partial sums s_0..s_{KS-2} (what the rows seen so far have
+// contributed to the next KS-1 outputs) and a new row H costs KS multiply-adds per sample
+//   out = s_0 + K[KS-1] H,   s_i = s_{i+1} + K[KS-2-i] H,   s_{KS-2} = K[0] H + 2^15
+// with no window to rotate and no separate rounding step; the result is bits 16..23 of out.
+// (Round 2, first version: vertical pass first in 16-bit lanes, then TWO horizontal passes -- shuffles and stride-CN
+// gathers included -- over the high and low bytes of the vertical sums: 258 instructions per row at 5x5, now 185.)
 // ---------------------------------------------------------------------------------------
 template <int CN, int KS>
 struct GaussQ8Op {
@@ -20,16 +24,13 @@ struct GaussQ8Op {
   static constexpr int P = KS / 2;
   static constexpr int E = CN;
   static constexpr int NOUT = 1;
-  static constexpr int WIN = KS == 3 ? 2 : KS == 5 ? 4 : 8;  // window slots (power of two >= KS-1)
-  // Rows unrolled in the hot loop = window period (measured: 3x3 69% vs 64% of the roofline at 8).
-  // 7x7: an 8-row unroll is a 42 KB loop (> 32 KB I-cache: 44% of stalls were instruction fetch), so
-  // its window is shifted physically instead (6 rows x 8 register moves per row) and the loop is 1 row.
-  static constexpr bool SHIFT = (KS == 7);
-  static constexpr int UNROLL = SHIFT ? 1 : WIN;
-  static constexpr int EXT = (HV * CN + 3) / 4;              // neighbour words needed on each side
+  static constexpr int NS = KS - 1;  // partial sums per sample
+  static constexpr int UNROLL = 2;   // no rotating window: the hot loop is as short as the instruction cache likes
+  static constexpr bool HOIST_WARM = true;
+  static constexpr int EXT = (HV * CN + 3) / 4;  // neighbour words needed on each side
   static_assert(KS == 3 || KS == 5 || KS == 7, "kernel size");
   static_assert(EXT <= 3, "taps beyond three words");
-  uint32_t win[WIN][8];
+  uint32_t sa[NS][8], sb[NS][8];  // partial sums of the low / high 16-bit lane's sample of register pair h
   uint32_t kx[HV + 1], ky[HV + 1];
 
   __device__ __forceinline__ void init(const StripParams &p) {
@@ -39,12 +40,7 @@ struct GaussQ8Op {
       ky[i] = p.taps_y[i];
     }
   }
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < WIN; ++j)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) win[j][h] = 0;
-  }
+  __device__ __forceinline__ void reset() {}  // the 2*HV warm-up rows overwrite every partial sum
 
   // symmetric KS-tap sum of packed pairs: t[0..KS-1]
   __device__ __forceinline__ uint32_t sym(const uint32_t (&t)[KS], const uint32_t (&k)[HV + 1]) const {
@@ -55,21 +51,22 @@ struct GaussQ8Op {
   }
 
   // neighbour words by shuffle, odd-phase pairs by PRMT, then the KS taps of every output pair
-  __device__ __forceinline__ void hpass(const uint32_t (&X)[8], uint32_t (&out)[8]) const {
+  __device__ __forceinline__ void hpass(const uint4 &q, uint32_t (&out)[8]) const {
     constexpr int NWD = 4 + 2 * EXT;  // words -EXT .. 3+EXT at index +EXT
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t lo[NWD], hi[NWD], loS[NWD - 1], hiS[NWD - 1];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      lo[k + EXT] = X[2 * k];
-      hi[k + EXT] = X[2 * k + 1];
+      lo[k + EXT] = __byte_perm(w[k], 0, 0x4240);  // (b0, b2) as 16-bit lanes
+      hi[k + EXT] = __byte_perm(w[k], 0, 0x4341);  // (b1, b3)
     }
 #pragma unroll
     for (int e = 0; e < EXT; ++e) {
       // left lane's words 4-EXT+e -> our word -EXT+e ; right lane's word e -> our word 4+e
-      lo[e] = __shfl_up_sync(0xffffffffu, X[2 * (4 - EXT + e)], 1);
-      hi[e] = __shfl_up_sync(0xffffffffu, X[2 * (4 - EXT + e) + 1], 1);
-      lo[4 + EXT + e] = __shfl_down_sync(0xffffffffu, X[2 * e], 1);
-      hi[4 + EXT + e] = __shfl_down_sync(0xffffffffu, X[2 * e + 1], 1);
+      lo[e] = __shfl_up_sync(0xffffffffu, lo[4 + e], 1);
+      hi[e] = __shfl_up_sync(0xffffffffu, hi[4 + e], 1);
+      lo[4 + EXT + e] = __shfl_down_sync(0xffffffffu, lo[EXT + e], 1);
+      hi[4 + EXT + e] = __shfl_down_sync(0xffffffffu, hi[EXT + e], 1);
     }
 #pragma unroll
     for (int i = 0; i < NWD - 1; ++i) {
@@ -87,70 +84,55 @@ struct GaussQ8Op {
           const int wd = p >> 2, ph = p & 3;
           t[j] = ph == 0 ? lo[wd] : ph == 1 ? hi[wd] : ph == 2 ? loS[wd] : hiS[wd];
         }
-        out[2 * k + e] = sym(t, kx);
+        out[2 * k + e] = sym(t, kx);  // <= 65280 per lane
       }
   }
 
-  // SHIFT: win[0] is the oldest row and win[KS-2] the newest; otherwise slot = feed index mod WIN
-  __device__ __forceinline__ void push(int slot, const uint32_t (&in)[8]) {
-    if (SHIFT) {
+  // K[i], i = 0..KS-1: the full (symmetric) vertical tap array
+  __device__ __forceinline__ uint32_t K(int i) const { return ky[i <= HV ? i : KS - 1 - i]; }
+
+  // One row into the partial sums of one sample.  LIVE = how many sums (from the back) already hold something:
+  // row j of a band has LIVE = j, so its warm-up costs j + 1 multiply-adds instead of KS.
+  template <int LIVE, bool EMIT>
+  __device__ __forceinline__ uint32_t vstep(uint32_t (&s)[NS][8], int h, uint32_t x) const {
+    uint32_t out = 0;
+    if (EMIT) out = s[0][h] + K(KS - 1) * x;
 #pragma unroll
-      for (int i = 0; i < KS - 2; ++i)
-#pragma unroll
-        for (int h = 0; h < 8; ++h) win[i][h] = win[i + 1][h];
-#pragma unroll
-      for (int h = 0; h < 8; ++h) win[KS - 2][h] = in[h];
-    } else {
-#pragma unroll
-      for (int h = 0; h < 8; ++h) win[slot][h] = in[h];
-    }
+    for (int i = 0; i < NS - 1; ++i)
+      if (NS - 1 - i <= LIVE) s[i][h] = s[i + 1][h] + K(KS - 2 - i) * x;
+    s[NS - 1][h] = K(0) * x + 0x8000u;
+    return out;
   }
 
+  // The first 2*HV rows of a band only build the sums (J8 = the row of the band: the skeleton hoists them).
   template <int J8>
   __device__ __forceinline__ void warm(const uint4 &q) {
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint32_t in[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      in[2 * k] = __byte_perm(w[k], 0, 0x4240);
-      in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);
-    }
-    push(J8 & (WIN - 1), in);
-  }
-
-  // J8 = (feed index) & 7, compile time
-  template <int J8, bool FAST>
-  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    constexpr int J = J8 & (WIN - 1);
-    uint32_t in[8];
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      in[2 * k] = __byte_perm(w[k], 0, 0x4240);
-      in[2 * k + 1] = __byte_perm(w[k], 0, 0x4341);
-    }
-    uint32_t Vh[8], Vl[8];
+    uint32_t H[8];
+    hpass(q, H);
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
-      uint32_t t[KS];
-#pragma unroll
-      for (int i = 0; i < KS - 1; ++i) t[i] = SHIFT ? win[i][h] : win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][h];  // oldest first
-      t[KS - 1] = in[h];
-      const uint32_t V = sym(t, ky);  // <= 65280 per lane
-      Vl[h] = V & 0x00FF00FFu;
-      Vh[h] = (V >> 8) & 0x00FF00FFu;
+      vstep<(J8 < NS ? J8 : NS), false>(sa, h, H[h] & 0xFFFFu);
+      vstep<(J8 < NS ? J8 : NS), false>(sb, h, H[h] >> 16);
     }
-    push(J, in);
+  }
+
+  template <int J8, bool FAST>
+  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
+    uint32_t H[8], ra[8], rb[8];
+    hpass(q, H);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      ra[h] = vstep<NS, true>(sa, h, H[h] & 0xFFFFu);
+      rb[h] = vstep<NS, true>(sb, h, H[h] >> 16);
+    }
     if (!FAST && !emit) return;
-    uint32_t A[8], B[8];
-    hpass(Vh, A);
-    hpass(Vl, B);
+    // pair 2k holds bytes (4k, 4k+2) of the row, pair 2k+1 bytes (4k+1, 4k+3); each result is byte 2 of its register
     uint32_t ow[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t H0 = A[2 * k] + ((B[2 * k] >> 8) & 0x00FF00FFu) + 0x00800080u;
-      const uint32_t H1 = A[2 * k + 1] + ((B[2 * k + 1] >> 8) & 0x00FF00FFu) + 0x00800080u;
-      ow[k] = __byte_perm(H0, H1, 0x7351);
+      const uint32_t e02 = __byte_perm(ra[2 * k], rb[2 * k], 0x0062);          // (byte 4k, byte 4k+2, 0, 0)
+      const uint32_t e13 = __byte_perm(ra[2 * k + 1], rb[2 * k + 1], 0x0062);  // (byte 4k+1, byte 4k+3, 0, 0)
+      ow[k] = __byte_perm(e02, e13, 0x5140);
     }
     uint8_t *o = outp[0];
     if (FAST) {
@@ -173,11 +155,13 @@ static inline int launch_gaussq8_ks(Ctx *c, const DBatch &src, const DBatch &dst
     tx[i] = kx[i];
     ty[i] = ky[i];
   }
+  // 7x7 keeps 6 partial sums for each of 16 samples (96 registers): 12 warps per CTA at <= 168 registers each
+  constexpr int NW = KS == 7 ? 12 : kNW;
   switch (src.v.cn) {
-    case 1: return launch_strip<GaussQ8Op<1, KS>>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
-    case 2: return launch_strip<GaussQ8Op<2, KS>>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
-    case 3: return launch_strip<GaussQ8Op<3, KS>>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
-    case 4: return launch_strip<GaussQ8Op<4, KS>>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
+    case 1: return launch_strip<GaussQ8Op<1, KS>, kS, NW>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
+    case 2: return launch_strip<GaussQ8Op<2, KS>, kS, NW>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
+    case 3: return launch_strip<GaussQ8Op<3, KS>, kS, NW>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
+    case 4: return launch_strip<GaussQ8Op<4, KS>, kS, NW>(c, src, &dst, 1, "gauss.band_rows", s, tx, ty);
   }
   return RCV_ERR_UNSUPPORTED;
 }

@@ -98,9 +98,10 @@ __device__ __forceinline__ uint32_t madc(uint32_t a, uint32_t c) {  // a * M + c
 //   Op::BAND_ROWS  output rows per work item when the job is large (default 40 - 2*HV);
 //   Op::EDGES the op applies the horizontal border itself (on its vertical sums, in registers) and is told
 //             per item where the row's edges are: op.edges(left_edge, right_edge, xr, lane);
-//   Op::HOIST_WARM  the first chunk of a band (2*HV window-filling rows, then R - 2*HV emitting rows) gets its own
-//             straight-line copy of the row bodies, so the steady-state loop carries no warm-up tests (ops whose row
-//             body is short enough that the second copy still fits the instruction cache);
+//   Op::HOIST_WARM  the steady-state loop carries no warm-up tests: the 2*HV window-filling rows of a band's first
+//             chunk run as straight-line code (warm<j> with j = the row of the band) and the loop takes over after
+//             them; an op whose UNROLL does not divide 2*HV (the 5x5 binomial: the whole chunk) gets a straight-line
+//             copy of the first chunk's emitting rows as well;
 //   Op::UNROLL_SLOW  rows unrolled in the per-row-tested loop (default UNROLL): ops without a rotating register
 //             window can keep that rarely used loop small;
 //   Op::MACRO horizontal border elements are macro-pixels reflected INCLUDING the edge element
@@ -316,7 +317,26 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
         // unrolling all 8 rows of the wider ops would not fit the 32 KB instruction cache.
         constexpr int U = Op::UNROLL;
         static_assert(R % U == 0, "window period must divide the chunk");
-        if constexpr (OpHoistWarm<Op>::value) {
+        int g0 = 0;
+        if constexpr (OpHoistWarm<Op>::value && (2 * HV) % U == 0) {
+          if (c == 0) {  // the band's first 2*HV rows fill the window, straight-line; the steady loop takes over after them
+            const uint32_t rowaddr = tile + lane * kLaneBytes;
+#pragma unroll
+            for (int j = 0; j < 2 * HV; ++j) {
+              const uint4 q = lds128(rowaddr + j * kTileBytes);
+              if (j == 0) op.template warm<0>(q);
+              if (j == 1) op.template warm<1>(q);
+              if (j == 2) op.template warm<2>(q);
+              if (j == 3) op.template warm<3>(q);
+              if (j == 4) op.template warm<4>(q);
+              if (j == 5) op.template warm<5>(q);
+              if (j == 6) op.template warm<6>(q);
+              if (j == 7) op.template warm<7>(q);
+            }
+            g0 = 2 * HV / U;
+          }
+        }
+        if constexpr (OpHoistWarm<Op>::value && (2 * HV) % U != 0) {
           if (c == 0) {  // the band's first chunk, straight-line: 2*HV rows fill the window, the rest emit
             const uint32_t rowaddr = tile + lane * kLaneBytes;
 #pragma unroll
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
           }
         }
 #pragma unroll 1
-        for (int g = 0; g < R / U; ++g) {
+        for (int g = g0; g < R / U; ++g) {
           const uint32_t rowaddr = tile + (uint32_t)(g * U) * kTileBytes + lane * kLaneBytes;
 #pragma unroll
           for (int j = 0; j < U; ++j) {

@@ -33,20 +33,17 @@ struct YuyvGauss5Op {
   static constexpr int OMUL = 3, ODIV = 2;
   static constexpr int BAND_ROWS = 60;  // measured best of 28..124 (heavier rows: fewer re-converted warm-up rows)
   static constexpr int NOUT = 1;
-  static constexpr int UNROLL = 4;  // window period; 8 rows would not fit the instruction cache
-  // ~300 instructions per row: with a second (unpredicated) copy of the row loop next to the general one the
-  // kernel's working set passed 32 KB and 20 % of the issue slots starved (stall_no_inst, r1 ncu capture)
-  static constexpr bool SINGLE_PATH = true;
-  uint32_t win[4][12];              // last 4 converted rows: [3k + c] = channel c (B, G, R) of macro-pixel k
+  // Vertical pass in transposed form (see Gauss5Op): partial sums instead of a rotating window of rows, so the loops
+  // need no particular unroll count.  Two rows per iteration keep the steady loop (~240 instructions per row), the
+  // per-row-tested loop and the four straight-line warm-up rows together inside the 32 KB instruction cache -- with the
+  // 4-row windowed form only ONE (predicated) copy of the row loop fitted (r1 ncu capture: stall_no_inst 20 %).
+  static constexpr int UNROLL = 2;
+  static constexpr bool HOIST_WARM = true;
+  uint32_t s1[12], s2[12], s3[12], s4[12];  // [3k + c] = channel c (B, G, R) of macro-pixel k, see Gauss5Op
   int left_lane, edge_lane, edge_m;  // lane to patch at the left edge / right edge (-1: none), m of the right edge
 
   __device__ __forceinline__ void init(const StripParams &) {}
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 12; ++h) win[j][h] = 0;
-  }
+  __device__ __forceinline__ void reset() {}  // four warm-up rows overwrite every partial sum
 
   // xr = tile byte offset of the first byte past the row (16 = start of lane 1)
   __device__ __forceinline__ void edges(bool left, bool right, int xr, int) {
@@ -70,59 +67,67 @@ struct YuyvGauss5Op {
   }
 
   template <int J8>
-  __device__ __forceinline__ void warm(const uint4 &q) {
-    convert(q, win[J8 & 3]);
+  __device__ __forceinline__ void warm(const uint4 &q) {  // J8 = row of the band (0..3): J8 operations per pair
+    uint32_t in[12];
+    convert(q, in);
+#pragma unroll
+    for (int h = 0; h < 12; ++h) {
+      if (J8 >= 3) s1[h] = madc<4>(in[h], s2[h]);
+      if (J8 >= 2) s2[h] = madc<6>(in[h], s3[h]);
+      if (J8 >= 1) s3[h] = madc<4>(in[h], s4[h]);
+      s4[h] = in[h];
+    }
   }
 
   template <int J8, bool FAST>
   __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    constexpr int J = J8 & 3;
     uint32_t in[12];
     convert(q, in);
-    if (!emit) {  // warm-up rows of a band only fill the window
-#pragma unroll
-      for (int h = 0; h < 12; ++h) win[J][h] = in[h];
-      return;
-    }
     // vertical: V = r0 + 4 r1 + 6 r2 + 4 r3 + r4 (+8 per lane = the final +128 after the 16-weight row pass)
     uint32_t V[12];
 #pragma unroll
     for (int h = 0; h < 12; ++h) {
-      const uint32_t r0 = win[J][h], r1 = win[(J + 1) & 3][h], r2 = win[(J + 2) & 3][h], r3 = win[(J + 3) & 3][h];
-      const uint32_t a = add3(r0, in[h], 0x00080008u);
-      const uint32_t b = add2(r1, r3);
-      V[h] = madc<6>(r2, madc<4>(b, a));
-      win[J][h] = in[h];
+      V[h] = add3(s1[h], in[h], 0x00080008u);
+      s1[h] = madc<4>(in[h], s2[h]);
+      s2[h] = madc<6>(in[h], s3[h]);
+      s3[h] = madc<4>(in[h], s4[h]);
+      s4[h] = in[h];
     }
+    if (!FAST && !emit) return;  // warm-up rows of a band only build the sums
     const int lane = threadIdx.x & 31;
     uint32_t Hc[3][4];
+    uint32_t Pp[3][6], Qq[3][5];  // per channel: P[-1..4] at index +1, Q[-1..3] at index +1
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      uint32_t Pp[6], Qq[5];  // P[-1..4] at index +1, Q[-1..3] at index +1
 #pragma unroll
-      for (int k = 0; k < 4; ++k) Pp[k + 1] = V[3 * k + c];
-      Pp[0] = __shfl_up_sync(0xffffffffu, Pp[4], 1);
-      Pp[5] = __shfl_down_sync(0xffffffffu, Pp[1], 1);
+      for (int k = 0; k < 4; ++k) Pp[c][k + 1] = V[3 * k + c];
+      Pp[c][0] = __shfl_up_sync(0xffffffffu, Pp[c][4], 1);
+      Pp[c][5] = __shfl_down_sync(0xffffffffu, Pp[c][1], 1);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) Qq[k] = __byte_perm(Pp[k], Pp[k + 1], 0x5432);
-      if (left_lane >= 0 || edge_lane >= 0) {  // warp-uniform: edge strips only.  Selects, not indexed stores.
-        const bool el = lane == left_lane, er = lane == edge_lane;
-        const uint32_t lp = swap16(Qq[1]), lq = swap16(Pp[1]);
-        Pp[0] = el ? lp : Pp[0];
-        Qq[0] = el ? lq : Qq[0];
+      for (int k = 0; k < 5; ++k) Qq[c][k] = __byte_perm(Pp[c][k], Pp[c][k + 1], 0x5432);
+    }
+    if (left_lane >= 0 || edge_lane >= 0) {  // warp-uniform: edge strips only (one branch per row).  Selects, not indexed stores.
+      const bool el = lane == left_lane, er = lane == edge_lane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t lp = swap16(Qq[c][1]), lq = swap16(Pp[c][1]);
+        Pp[c][0] = el ? lp : Pp[c][0];
+        Qq[c][0] = el ? lq : Qq[c][0];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const bool hit = er && edge_m == m;
-          const uint32_t np = swap16(Qq[m]);      // P[m+1] = swap(Q[m-1])
-          const uint32_t nq = swap16(Pp[m + 1]);  // Q[m]   = swap(P[m])
-          Pp[m + 2] = hit ? np : Pp[m + 2];
-          Qq[m + 1] = hit ? nq : Qq[m + 1];
+          const uint32_t np = swap16(Qq[c][m]);      // P[m+1] = swap(Q[m-1])
+          const uint32_t nq = swap16(Pp[c][m + 1]);  // Q[m]   = swap(P[m])
+          Pp[c][m + 2] = hit ? np : Pp[c][m + 2];
+          Qq[c][m + 1] = hit ? nq : Qq[c][m + 1];
         }
       }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        Hc[c][k] = madc<6>(Pp[k + 1], madc<4>(add2(Qq[k], Qq[k + 1]), add2(Pp[k], Pp[k + 2])));  // <= 65408 per lane
-    }
+        Hc[c][k] = madc<6>(Pp[c][k + 1], madc<4>(add2(Qq[c][k], Qq[c][k + 1]), add2(Pp[c][k], Pp[c][k + 2])));  // <= 65408 per lane
     // pack: the result bytes are the high bytes of the 16-bit lanes; two macro-pixels -> 12 bytes = 3 words
     uint32_t ow[6];
 #pragma unroll
