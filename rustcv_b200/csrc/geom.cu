@@ -82,6 +82,7 @@ struct ResizeArgs {
   int srows, scols, drows, dcols, cn;
   const ResizeCol *cols;
   const ResizeRow *rows;
+  const int2 *cols8;  // compact u8 column table: .x = x0, .y = a0 | a1 << 16 (k_resize_u8w)
 };
 
 template <typename T>
@@ -164,22 +165,28 @@ __global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
 template <int CN>
 __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
   static_assert(CN == 3 || CN == 4, "BGR / BGRA");
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 destination pixels
-  const int dy = blockIdx.y;
+  // block = 32 groups x 4 rows: a warp is 32 consecutive groups of one row, and a row of G groups wastes at most
+  // 31 threads (128 groups x 1 row left 1280- and 1600-column rows with 17 % / 22 % of the threads idle)
+  const int t = blockIdx.x * 32 + (threadIdx.x & 31);  // group of 4 destination pixels
+  const int dy = blockIdx.y * 4 + (threadIdx.x >> 5);
   const int dx0 = 4 * t;
-  if (dx0 >= a.dcols) return;
+  if (dx0 >= a.dcols || dy >= a.drows) return;
   const ResizeRow r = a.rows[dy];
   const uint8_t *src = a.src + (size_t)blockIdx.z * a.sfs;
   const uint32_t *s0 = (const uint32_t *)(src + (size_t)r.y0 * a.sstep);
   const uint32_t *s1 = (const uint32_t *)(src + (size_t)r.y1 * a.sstep);
   const int last_word = (a.scols * CN - 1) >> 2;  // the last word holding row bytes
+  const uint32_t b0s = (uint32_t)r.b0 << 16, b1s = (uint32_t)r.b1 << 16;
   uint32_t ob[4 * CN];                            // output bytes of the 4 pixels
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int dx = min(dx0 + q, a.dcols - 1);  // a ragged last group recomputes its last pixel (not stored)
-    const int2 xx = *(const int2 *)&a.cols[dx].x0;
-    const int2 aa = *(const int2 *)&a.cols[dx].a0;
-    const int o = xx.x * CN, wi = o >> 2, sh = (o & 3) * 8;
+    // one 8-byte table entry per destination column (the 24-byte ResizeCol cost a warp 12 L1 wavefronts per pixel
+    // column, this costs 2)
+    const int2 e = __ldg(a.cols8 + dx);
+    const int x0 = e.x;
+    const int2 aa = make_int2(e.y & 0xFFFF, (int)((unsigned)e.y >> 16));
+    const int o = x0 * CN, wi = o >> 2, sh = (o & 3) * 8;
     uint32_t p0[2][CN], p1[2][CN];  // [row][channel]: tap (x0) and tap (x1)
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
@@ -190,24 +197,29 @@ __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
         lo = w0;  // o is a multiple of 4: the two pixels are the two words
         hi = w1;
       } else {
-        const uint32_t w2 = __ldg(row + min(wi + 2, last_word));
+        // bytes o .. o+5: a third word only when the first tap starts at byte 3 of its word
+        uint32_t w2 = 0;
+        if (sh == 24) w2 = __ldg(row + min(wi + 2, last_word));
         lo = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
         hi = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
       }
+      // one PRMT per tap byte (shift + mask were two ALU-pipe operations each, and that pipe is this kernel's limit:
+      // profiles/r2_resize_general_ncu_before.txt, ALU 85 % busy).  A column clamped at the right edge has
+      // a0 = 2048, a1 = 0 in the compact table, so its second tap (whatever lies there) contributes nothing.
 #pragma unroll
       for (int ch = 0; ch < CN; ++ch) {
-        p0[rr][ch] = (lo >> (8 * ch)) & 0xFFu;
+        p0[rr][ch] = __byte_perm(lo, 0, 0x4440 | ch);
         const int k = CN + ch;  // byte index of the second tap
-        p1[rr][ch] = ((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4)))) & 0xFFu;
-        if (xx.y == xx.x) p1[rr][ch] = p0[rr][ch];  // clamped at the right edge: x1 == x0
+        p1[rr][ch] = k < 4 ? __byte_perm(lo, 0, 0x4440 | k) : __byte_perm(hi, 0, 0x4440 | (k - 4));
       }
     }
 #pragma unroll
     for (int ch = 0; ch < CN; ++ch) {
-      const int S0 = (int)p0[0][ch] * aa.x + (int)p1[0][ch] * aa.y;
-      const int S1 = (int)p0[1][ch] * aa.x + (int)p1[1][ch] * aa.y;
-      const int v = (((r.b0 * (S0 >> 4)) >> 16) + ((r.b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-      ob[q * CN + ch] = (uint32_t)min(max(v, 0), 255);
+      const uint32_t S0 = p0[0][ch] * (uint32_t)aa.x + p1[0][ch] * (uint32_t)aa.y;
+      const uint32_t S1 = p0[1][ch] * (uint32_t)aa.x + p1[1][ch] * (uint32_t)aa.y;
+      // (b * (S >> 4)) >> 16 as the high word of (b << 16) * (S >> 4): one multiply, no shift
+      const uint32_t v = (__umulhi(S0 >> 4, b0s) + __umulhi(S1 >> 4, b1s) + 2u) >> 2;
+      ob[q * CN + ch] = min(v, 255u);  // v <= 255 whenever the weights sum to 2048; kept for the oracle's saturate
     }
   }
   uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep + (size_t)dx0 * CN;
@@ -383,7 +395,8 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
   }
   // the per-column / per-row tables depend on the geometry only: rebuilt and uploaded when it changes
   void *dcols = nullptr, *drows = nullptr;
-  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, (size_t)dst.v.cols * sizeof(ResizeCol), &dcols));
+  const size_t cols8_off = ((size_t)dst.v.cols * sizeof(ResizeCol) + 15) & ~(size_t)15;
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, cols8_off + (size_t)dst.v.cols * sizeof(int2), &dcols));
   RCV_TRY(ctx_scratch(c, SCR_TABLE_Y, (size_t)dst.v.rows * sizeof(ResizeRow), &drows));
   const int key[4] = {src.v.rows, src.v.cols, dst.v.rows, dst.v.cols};
   if (memcmp(key, c->resize_key, sizeof(key)) != 0) {
@@ -391,12 +404,18 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
     std::vector<ResizeRow> rows;
     resize_tables(src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, cols, rows);
     RCV_CUDA(cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(ResizeCol), cudaMemcpyHostToDevice, s));
+    std::vector<int2> cols8(cols.size());
+    for (size_t i = 0; i < cols.size(); ++i)
+      cols8[i] = cols[i].x1 == cols[i].x0 ? make_int2(cols[i].x0, cols[i].a0 + cols[i].a1)  // clamped: one tap takes both weights
+                                          : make_int2(cols[i].x0, cols[i].a0 | (cols[i].a1 << 16));
+    RCV_CUDA(cudaMemcpyAsync((uint8_t *)dcols + cols8_off, cols8.data(), cols8.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     RCV_CUDA(cudaMemcpyAsync(drows, rows.data(), rows.size() * sizeof(ResizeRow), cudaMemcpyHostToDevice, s));
     // the vectors die at return: do not depend on how the driver stages pageable sources
     RCV_CUDA(cudaStreamSynchronize(s));
     memcpy(c->resize_key, key, sizeof(key));
   }
   a.cols = (const ResizeCol *)dcols;
+  a.cols8 = (const int2 *)((const uint8_t *)dcols + cols8_off);
   a.rows = (const ResizeRow *)drows;
   // u8 BGR / BGRA with word-aligned rows on both sides: the word-load kernel (rows must be readable up to the
   // word that holds their last byte: step >= row bytes rounded up to 4)
@@ -404,7 +423,7 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
       opt_get("resize.byte_loads", 0) == 0 && ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 3) == 0) &&
       ((((uintptr_t)dst.v.data | dst.v.step | dst.frame_stride) & 3) == 0) &&
       src.v.step >= (((size_t)src.v.cols * src.v.cn + 3) & ~(size_t)3)) {
-    dim3 gridw(ceil_div(ceil_div(dst.v.cols, 4), 128), dst.v.rows, src.n);
+    dim3 gridw(ceil_div(ceil_div(dst.v.cols, 4), 32), ceil_div(dst.v.rows, 4), src.n);
     if (src.v.cn == 3)
       k_resize_u8w<3><<<gridw, 128, 0, s>>>(a);
     else
