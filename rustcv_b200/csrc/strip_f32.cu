@@ -15,6 +15,7 @@ struct SepF32Op {
   static constexpr int NOUT = 1;
   static constexpr int WIN = KS == 3 ? 2 : KS == 5 ? 4 : 8;
   static constexpr int UNROLL = WIN;
+  static constexpr bool HOIST_WARM = KS <= 5;  // 2*HV == UNROLL: the window-filling rows run outside the steady loop
   float win[WIN][4];  // row-filtered previous rows
   float kx[KS], ky[KS];
 

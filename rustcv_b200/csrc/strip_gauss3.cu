@@ -19,6 +19,7 @@ struct Gauss3Op {
   static constexpr int E = CN;
   static constexpr int NOUT = 1;
   static constexpr int UNROLL = 8;  // window period 2; whole chunks unrolled like Gauss5Op
+  static constexpr bool HOIST_WARM = true;  // like Gauss5Op: a straight-line copy of the band's first chunk
   uint32_t win[2][8];               // last 2 rows, unpacked: [2w] = bytes 0,2 of word w; [2w+1] = bytes 1,3
 
   __device__ __forceinline__ void init(const StripParams &) {}
