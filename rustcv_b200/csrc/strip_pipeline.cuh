@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
   constexpr uint32_t kStageBytes = R * kTileBytes;
   extern __shared__ __align__(128) uint8_t smem_raw[];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the ring / barrier addresses, the item
+  // decode and the TMA operands on the uniform datapath (no R2UR + ELECT waterfall around UTMALDG)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t tiles = smem_u32(smem_raw) + (uint32_t)warp * S * kStageBytes;
   const uint32_t bars = smem_u32(smem_raw) + (uint32_t)NW * S * kStageBytes + (uint32_t)warp * S * 8;
 
