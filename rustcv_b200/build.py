@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "librcv_imgproc.so")
 SOURCES = ["context.cu", "hostmem.cu", "multi.cu", "tma.cu", "cvt.cu", "strip_gauss5.cu", "strip_gauss3.cu", "strip_gaussq8_k3.cu", "strip_gaussq8_k5.cu", "strip_gaussq8_k7.cu", "strip_gaussq8_k9.cu", "strip_gaussq8_k11.cu", "strip_gaussq8_k13.cu", "strip_gaussq8_k15.cu", "strip_sobel.cu", "strip_f32.cu", "strip_f32cn.cu", "strip_f32wide.cu", "strip_f2d_u8.cu", "strip_yuyv_sobel.cu", "strip_yuyv_gauss5.cu", "filter.cu", "geom.cu", "mjpeg.cu", "abi.cu"]
-HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(CSRC, "strip_pipeline.cuh"),
+HEADERS = [os.path.join(CSRC, "rcv_internal.cuh"), os.path.join(CSRC, "fastdiv.h"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(CSRC, "strip_pipeline.cuh"),
            os.path.join(CSRC, "strip_gaussq8.cuh"), os.path.join(CSRC, "strip_gaussq8_wide.cuh"), os.path.join(CSRC, "strip_f32_gather.cuh"), os.path.join(CSRC, "cvt_math.cuh"), os.path.join(HERE, "..", "include", "rcv_imgproc.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -136,15 +136,11 @@ __global__ void __launch_bounds__(128) k_yuv422_vec(CvtArgs a) {
     if (CODE == RCV_COLOR_YUYV2GRAY) {
       uint32_t gr[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t gy[4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          Px6 o = yuv_word<false>(in[2 * k + h]);
-          gy[2 * h] = gray_of(o.b0 >> 8, o.g0 >> 8, o.r0 >> 8);
-          gy[2 * h + 1] = gray_of(o.b1 >> 8, o.g1 >> 8, o.r1 >> 8);
-        }
-        gr[k] = gy[0] | (gy[1] << 8) | (gy[2] << 16) | (gy[3] << 24);
+      for (int k = 0; k < 4; ++k) {  // two macro-pixels -> 4 gray bytes, two pixels per operation (cvt_math.cuh)
+        uint32_t b0, g0, r0, b1, g1, r1;
+        yuv_word_pairs<false>(in[2 * k], b0, g0, r0);
+        yuv_word_pairs<false>(in[2 * k + 1], b1, g1, r1);
+        gr[k] = __byte_perm(gray_pair(b0, g0, r0), gray_pair(b1, g1, r1), 0x6420);
       }
       *(uint4 *)(d + (size_t)g * 16) = make_uint4(gr[0], gr[1], gr[2], gr[3]);
     } else {

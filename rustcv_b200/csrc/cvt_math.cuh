@@ -67,4 +67,17 @@ __device__ __forceinline__ void yuv_word_pairs(uint32_t w, uint32_t &pb, uint32_
   pr = __vimin_s16x2_relu(__byte_perm(mad298(y0, dr), mad298(y1, dr), 0x6521), 0x00FF00FFu);
 }
 
+// BGR2GRAY of two pixels at once, on the (pixel 0, pixel 1) 16-bit-lane pairs yuv_word_pairs hands out.  The 15-bit
+// coefficients split into bytes -- 3735 = 14*256 + 151, 19235 = 75*256 + 35, 9798 = 38*256 + 70, high parts summing
+// to 127 and low parts to 256 -- so A = 14b + 75g + 38r <= 32385 and B = 151b + 35g + 70r <= 65280 both fit a lane, and
+//   (3735b + 19235g + 9798r + 16384) >> 15  ==  (256A + B + 16384) >> 15  ==  (A + (B >> 8) + 64) >> 7
+// exactly (16384 = 64 * 256, and dropping B's low byte cannot carry across a multiple of 128 of an integer sum).
+// 9 operations per pixel pair instead of 2 x 7.  Result: (gray 0, gray 1) as 16-bit lanes, values 0..255.
+__device__ __forceinline__ uint32_t gray_pair(uint32_t pb, uint32_t pg, uint32_t pr) {
+  const uint32_t A = pb * 14u + pg * 75u + pr * 38u;
+  const uint32_t B = pb * 151u + pg * 35u + pr * 70u;
+  const uint32_t u = A + __byte_perm(B, 0, 0x4341) + 0x00400040u;
+  return (u >> 7) & 0x00FF00FFu;
+}
+
 }  // namespace rcv

@@ -31,6 +31,7 @@
 //     than the machine is cut so that its items fill one round (pick_band_rows).
 #pragma once
 
+#include "fastdiv.h"
 #include "rcv_internal.cuh"
 #include "tma_ptx.cuh"
 
@@ -452,25 +453,6 @@ static inline bool aligned16(const DBatch &b) {
 
 static inline bool strip_path_ok(const DBatch &src, int min_rows, int min_cols) {
   return aligned16(src) && src.v.rows >= min_rows && src.v.cols >= min_cols;
-}
-
-// n / d == umulhi(n, mul) >> sh for every n < n_max (Granlund-Montgomery round-up reciprocal, checked against its error
-// bound here); mul = 0 tells the kernel to divide.
-static inline void strip_fast_div(uint32_t d, uint64_t n_max, uint32_t *mul, uint32_t *sh) {
-  *mul = 0;
-  *sh = 0;
-  if (d < 2) return;
-  for (uint32_t s = 0; s < 32; ++s) {
-    const unsigned __int128 two = (unsigned __int128)1 << (32 + s);
-    const unsigned __int128 m = (two + d - 1) / d;  // ceil(2^(32+s) / d)
-    if (m >> 32) break;
-    const unsigned __int128 e = m * d - two;        // 0 <= e < d; exact while n * e < 2^(32+s)
-    if ((unsigned __int128)n_max * e < two) {
-      *mul = (uint32_t)m;
-      *sh = s;
-      return;
-    }
-  }
 }
 
 // Picks the band height.  Measured on B200 (profiles/README.md, sweep r1d): short bands win

@@ -33,3 +33,14 @@ def test_cpp_mirror_parity_on_gpu(oracle):
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_mirror ok" in out.stdout
+
+
+def test_item_decode_reciprocals_are_exact(tmp_path):
+    """csrc/fastdiv.h (the strip kernels decode item -> frame / band / strip with host-made reciprocals) vs real
+    division, compiled as plain C++."""
+    exe = str(tmp_path / "fastdiv_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", os.path.join(ROOT, "tests", "cpp", "fastdiv_test.cpp"),
+                           "-I", os.path.join(ROOT, "rustcv_b200", "csrc"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "fastdiv ok" in out.stdout

@@ -345,3 +345,13 @@ def test_tuned_cpu_gaussian_is_bit_identical_to_the_definition(oracle):
     assert (oracle.gaussian5_fast(p) == oracle.gaussian_blur(p, (5, 5))).all()
     img = oracle.fill_u8(2, 2160 * 3840 * 3).reshape(2160, 3840, 3)
     assert oracle.crc32(oracle.gaussian5_fast(img)) == 0x827081C8
+
+
+def test_gray_pair_byte_split_identity_exhaustive():
+    """cvt_math.cuh gray_pair: with 3735 = 14*256+151, 19235 = 75*256+35, 9798 = 38*256+70,
+    (3735b + 19235g + 9798r + 16384) >> 15 == (A + (B >> 8) + 64) >> 7 for every (b, g, r), and A, B fit 16 bits."""
+    b, g, r = np.meshgrid(np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64), indexing="ij")
+    A = 14 * b + 75 * g + 38 * r
+    B = 151 * b + 35 * g + 70 * r
+    assert A.max() <= 32385 and B.max() <= 65280 and (A + (B >> 8) + 64).max() < 65536
+    assert (((3735 * b + 19235 * g + 9798 * r + 16384) >> 15) == ((A + (B >> 8) + 64) >> 7)).all()

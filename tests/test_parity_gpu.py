@@ -163,6 +163,14 @@ def test_yuv_formula_exhaustive_on_gpu(rcv):
     assert (got[:, :, 0] == np.clip((298 * c0 + 516 * uu + 128) >> 8, 0, 255)).all()
     assert (got[:, :, 1] == np.clip((298 * c0 - 100 * uu - 208 * vv + 128) >> 8, 0, 255)).all()
     assert (got[:, :, 2] == np.clip((298 * c0 + 409 * vv + 128) >> 8, 0, 255)).all()
+    # YUYV -> Gray over the same 2^24 triples: the kernel computes two pixels per operation with the gray
+    # coefficients split into bytes (cvt_math.cuh gray_pair); the definition is OpenCV's 15-bit formula on the BGR above
+    dg = R.Mat.empty()
+    R.imgproc.cvt_color(R.Mat.from_numpy(frame.reshape(256, 65536 * 2, 2)), dg, R.imgproc.COLOR_YUYV2GRAY)
+    gray = dg.to_numpy().reshape(256, 65536, 2)
+    for k in (0, 1):
+        b, g, r = (got[:, :, 3 * k + i].astype(np.int32) for i in range(3))
+        assert (gray[:, :, k] == ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15)).all(), k
 
 
 @pytest.mark.parametrize("where", ["host", "device"])
