@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
 // makes 4 destination pixels so that its output leaves as words.  Same fixed-point arithmetic.
 template <int CN>
 __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
-  static_assert(CN == 3 || CN == 4, "BGR / BGRA");
+  static_assert(CN >= 1 && CN <= 4, "1..4 interleaved u8 channels");
   // block = 32 groups x 4 rows: a warp is 32 consecutive groups of one row, and a row of G groups wastes at most
   // 31 threads (128 groups x 1 row left 1280- and 1600-column rows with 17 % / 22 % of the threads idle)
   const int t = blockIdx.x * 32 + (threadIdx.x & 31);  // group of 4 destination pixels
@@ -191,17 +191,22 @@ __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const uint32_t *row = rr ? s1 : s0;
-      const uint32_t w0 = __ldg(row + wi), w1 = __ldg(row + min(wi + 1, last_word));
-      uint32_t lo, hi;
+      // the two taps are bytes o .. o + 2*CN - 1: one to three aligned words, shifted into place
+      const uint32_t w0 = __ldg(row + wi);
+      uint32_t lo, hi = 0;
       if (CN == 4) {
         lo = w0;  // o is a multiple of 4: the two pixels are the two words
-        hi = w1;
-      } else {
-        // bytes o .. o+5: a third word only when the first tap starts at byte 3 of its word
-        uint32_t w2 = 0;
+        hi = __ldg(row + min(wi + 1, last_word));
+      } else if (CN == 3) {
+        const uint32_t w1 = __ldg(row + min(wi + 1, last_word));
+        uint32_t w2 = 0;  // a third word only when the first tap starts at byte 3 of its word
         if (sh == 24) w2 = __ldg(row + min(wi + 2, last_word));
         lo = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
         hi = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
+      } else {
+        uint32_t w1 = 0;  // gray / 2 channels: the second word only when the taps straddle a word boundary
+        if (sh + 16 * CN > 32) w1 = __ldg(row + min(wi + 1, last_word));
+        lo = __funnelshift_r(w0, w1, sh);
       }
       // one PRMT per tap byte (shift + mask were two ALU-pipe operations each, and that pipe is this kernel's limit:
       // profiles/r2_resize_general_ncu_before.txt, ALU 85 % busy).  A column clamped at the right edge has
@@ -419,15 +424,17 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
   a.rows = (const ResizeRow *)drows;
   // u8 BGR / BGRA with word-aligned rows on both sides: the word-load kernel (rows must be readable up to the
   // word that holds their last byte: step >= row bytes rounded up to 4)
-  if (src.v.depth == RCV_U8 && (src.v.cn == 3 || src.v.cn == 4) && opt_get("resize.force_generic", 0) == 0 &&
+  if (src.v.depth == RCV_U8 && src.v.cn >= 1 && src.v.cn <= 4 && opt_get("resize.force_generic", 0) == 0 &&
       opt_get("resize.byte_loads", 0) == 0 && ((((uintptr_t)src.v.data | src.v.step | src.frame_stride) & 3) == 0) &&
       ((((uintptr_t)dst.v.data | dst.v.step | dst.frame_stride) & 3) == 0) &&
       src.v.step >= (((size_t)src.v.cols * src.v.cn + 3) & ~(size_t)3)) {
     dim3 gridw(ceil_div(ceil_div(dst.v.cols, 4), 32), ceil_div(dst.v.rows, 4), src.n);
-    if (src.v.cn == 3)
-      k_resize_u8w<3><<<gridw, 128, 0, s>>>(a);
-    else
-      k_resize_u8w<4><<<gridw, 128, 0, s>>>(a);
+    switch (src.v.cn) {
+      case 1: k_resize_u8w<1><<<gridw, 128, 0, s>>>(a); break;
+      case 2: k_resize_u8w<2><<<gridw, 128, 0, s>>>(a); break;
+      case 3: k_resize_u8w<3><<<gridw, 128, 0, s>>>(a); break;
+      default: k_resize_u8w<4><<<gridw, 128, 0, s>>>(a); break;
+    }
     count_launch();
     RCV_CUDA(cudaGetLastError());
     return RCV_OK;

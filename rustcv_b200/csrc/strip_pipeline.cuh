@@ -156,7 +156,8 @@ struct OpMacro<Op, std::void_t<decltype(Op::MACRO)>> { static constexpr int valu
 // the strip pipeline
 // ---------------------------------------------------------------------------------------
 template <class Op, int R, int S, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CUtensorMap tmap, const StripParams p) {
+__global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CUtensorMap tmap,
+                                                      const __grid_constant__ StripParams p) {
   static_assert((R == 8 || R == 16) && R >= 2 * Op::HV + 1,
                 "chunk rows: 8 (the ops' window rotation assumes it) or 16 for ops with more than 3 halo rows -- the border "
                 "patches read at most one chunk back");

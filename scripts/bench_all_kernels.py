@@ -103,8 +103,8 @@ def f2d_batch(srcs, dsts, k):
         I.filter2d(srcs[i], dsts[i], k)
 
 
-run("filter2D 3x3, 4K BGR u8, 8 launches of 1 frame [k_strip<Filter2dU8Op<3>>]", lambda: f2d_batch(bgr, out3, k3), 6 * 8 * H * W)
-run("filter2D 5x5, 4K BGR u8, 8 launches of 1 frame [k_filter2d<u8,5>]", lambda: f2d_batch(bgr, out3, np.ones((5, 5), np.float32) / 25), 6 * 8 * H * W)
+run("filter2D 3x3, 4K BGR u8, 8 launches of 1 frame [k_strip<Filter2dU8Op<3,3>>]", lambda: f2d_batch(bgr, out3, k3), 6 * 8 * H * W)
+run("filter2D 5x5, 4K BGR u8, 8 launches of 1 frame [k_strip<Filter2dU8Op<3,5>>]", lambda: f2d_batch(bgr, out3, np.ones((5, 5), np.float32) / 25), 6 * 8 * H * W)
 for b in (x4, yuyv, g1):
     b.free()
 # resize
@@ -113,6 +113,12 @@ for name, dr, dc, rows_used in (("4K->1080p (exact 2x) [k_resize2x_u8<3,8>]", 10
     d = R.Mat.device_batch(N, dr, dc, 3)
     run(f"resize {name}, BGR u8 x32", lambda: I.resize_batch(bgr, d), N * (rows_used * W * 3 + dr * dc * 3), "bytes = source rows touched + destination")
     d.free()
+gsrc = batch(N, H, W, 1, seed=7)
+for name, dr, dc in (("4K->720p (3x)", 720, 1280), ("4K->1600x900 (2.4x)", 900, 1600)):
+    d = R.Mat.device_batch(N, dr, dc, 1)
+    run(f"resize {name} [k_resize_u8w<1>], gray u8 x32", lambda: I.resize_batch(gsrc, d), N * (2 * dr * W + dr * dc), "bytes = source rows touched + destination")
+    d.free()
+gsrc.free()
 d8 = R.Mat.device_batch(8, 4320, 7680, 3)
 run("resize 4K->8K (exact 2x up) [k_resize_up2x_u8<3,4>], BGR u8 x8", lambda: I.resize_batch(bgr.mats[:8], d8), 8 * (H * W * 3 + 4320 * 7680 * 3))
 d8.free()

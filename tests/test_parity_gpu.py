@@ -448,7 +448,7 @@ def test_f32_strip_kernels(rcv, oracle, ks):
 
 @pytest.mark.parametrize("cn", [1, 2, 3, 4])
 def test_filter2d_u8_3x3_strip_kernel(rcv, oracle, cn):
-    """k_strip<Filter2dU8Op<CN>>: sharpen / Laplacian / random taps incl. exact .5 ties and saturation."""
+    """k_strip<Filter2dU8Op<CN,3>>: sharpen / Laplacian / random taps incl. exact .5 ties and saturation."""
     R = rcv
     rng = np.random.default_rng(cn)
     h, w = 203, 517
@@ -463,6 +463,38 @@ def test_filter2d_u8_3x3_strip_kernel(rcv, oracle, cn):
         for delta in (0.0, 0.5):
             R.imgproc.filter2d(s, d, k, delta=delta)
             assert_same(d.to_numpy(), oracle.filter2d(a, k, delta), f"filter2d u8 3x3 cn{cn} kernel{i} delta{delta}")
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [(203, 517), (8, 8), (41, 163), (77, 1000)])
+def test_filter2d_u8_5x5_strip_kernel(rcv, oracle, cn, shape):
+    """k_strip<Filter2dU8Op<CN,5>> (transposed form: pending row sums instead of a window of rows): unsharp mask
+    (saturates both ways), exact binary fractions (.5 ties round to even), an asymmetric ramp (catches any swap of tap
+    order or direction), random taps; several bands and strips, the 8x8 minimum, ragged right edges; and the strip
+    kernel against the general kernel."""
+    R = rcv
+    rng = np.random.default_rng(10 + cn)
+    h, w = shape
+    a = oracle.fill_u8(170 + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+    s = mats(R, a, "device")
+    d = s.like()
+    unsharp = -np.ones((5, 5), np.float32) / 8
+    unsharp[2, 2] = 4.0
+    kernels = [unsharp, np.full((5, 5), 0.03125, np.float32), (np.arange(25, dtype=np.float32).reshape(5, 5) - 7) / 64,
+               rng.normal(size=(5, 5)).astype(np.float32) / 5]
+    n0 = R.imgproc.launch_count()
+    for i, k in enumerate(kernels):
+        for delta in (0.0, 0.5):
+            R.imgproc.filter2d(s, d, k, delta=delta)
+            assert_same(d.to_numpy(), oracle.filter2d(a, k, delta), f"filter2d u8 5x5 cn{cn} {shape} kernel{i} delta{delta}")
+    assert R.imgproc.launch_count() - n0 == 8, "one strip launch per call"
+    R.imgproc.set_option("f2d.force_generic", 1)
+    try:
+        d2 = s.like()
+        R.imgproc.filter2d(s, d2, kernels[3], delta=0.5)
+        assert_same(d2.to_numpy(), d.to_numpy(), "strip op vs general kernel")
+    finally:
+        R.imgproc.set_option("f2d.force_generic", 0)
 
 
 @pytest.mark.parametrize("ksz", [(3, 3), (5, 5), (7, 3), (4, 4), (1, 1), (9, 9)])
