@@ -225,6 +225,9 @@ RCV_API int rcv_yuyv_to_sobel_mag_batch(const RcvMat *srcs_yuyv, RcvMat *mags_f3
 RCV_API int rcv_yuyv_to_bgr_gaussian5_batch(const RcvMat *srcs_yuyv, RcvMat *dsts_bgr, int32_t n);
 RCV_API int rcv_sep_filter2d_q8_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const int32_t *kx, int32_t kw,
                               const int32_t *ky, int32_t kh);
+/* dense filter2D (rcv_filter2d) over a batch: u8 or f32, kw x kh taps row-major, one launch for a uniform device batch */
+RCV_API int rcv_filter2d_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const float *kernel, int32_t kw, int32_t kh,
+                       float delta);
 
 /* ---- the same batches sharded over several GPUs -----
  * Frames are independent: host Mats go frame j -> GPU j mod ngpus, device Mats
@@ -245,6 +248,8 @@ RCV_API int rcv_yuyv_to_bgr_gaussian5_batch_multi(const RcvMat *srcs_yuyv, RcvMa
  * rcv_set_kernel_broadcast (kw taps for x, then kh taps for y). */
 RCV_API int rcv_sep_filter2d_q8_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus,
                                     const int32_t *kx, int32_t kw, const int32_t *ky, int32_t kh);
+RCV_API int rcv_filter2d_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus, const float *kernel,
+                             int32_t kw, int32_t kh, float delta);
 
 /* The path's single collective: filter coefficients are set up once, on GPU
  * `root_device`, and broadcast (ncclBroadcast over NVLink) into the coefficient

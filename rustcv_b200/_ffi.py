@@ -97,6 +97,8 @@ SIGNATURES = {
     "rcv_warp_affine_batch": [_MatP, _MatP, C.c_int32, _P(C.c_double), C.c_int32, C.c_double],
     "rcv_cvt_color_batch": [_MatP, _MatP, C.c_int32, C.c_int32],
     "rcv_sep_filter2d_q8_batch": [_MatP, _MatP, C.c_int32, _P(C.c_int32), C.c_int32, _P(C.c_int32), C.c_int32],
+    "rcv_filter2d_batch": [_MatP, _MatP, C.c_int32, _P(C.c_float), C.c_int32, C.c_int32, C.c_float],
+    "rcv_filter2d_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, _P(C.c_float), C.c_int32, C.c_int32, C.c_float],
     "rcv_gaussian_blur_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double],
     "rcv_sobel_mag_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],
     "rcv_resize_bilinear_batch_multi": [_MatP, _MatP, C.c_int32, C.c_int32],

@@ -891,6 +891,24 @@ int rcv_filter2d(const RcvMat *src, RcvMat *dst, const float *kernel, int32_t kw
   }, -1, band_window(kh / 2));
 }
 
+static int filter2d_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const float *kernel, int32_t kw, int32_t kh,
+                          float delta, int ngpus) {
+  RCV_TRY(check_batch(srcs, dsts, n, "filter2D"));
+  if (n == 0) return RCV_OK;
+  RCV_TRY(check_filter_pair(&srcs[0], &dsts[0], "filter2D"));
+  if (!kernel) return fail(RCV_ERR_ARG, "NULL kernel");
+  return run_batch(srcs, dsts, n, [=](Ctx *c, const DBatch &s, const DBatch &d, cudaStream_t st) {
+    return launch_filter2d(c, s, d, kernel, kw, kh, delta, st);
+  }, -1, band_window(kh / 2), ngpus);
+}
+int rcv_filter2d_batch(const RcvMat *srcs, RcvMat *dsts, int32_t n, const float *kernel, int32_t kw, int32_t kh, float delta) {
+  return filter2d_batch(srcs, dsts, n, kernel, kw, kh, delta, 0);
+}
+int rcv_filter2d_batch_multi(const RcvMat *srcs, RcvMat *dsts, int32_t n, int32_t ngpus, const float *kernel, int32_t kw,
+                             int32_t kh, float delta) {
+  return filter2d_batch(srcs, dsts, n, kernel, kw, kh, delta, ngpus > 0 ? ngpus : -1);
+}
+
 static int check_sobel(const RcvMat *src, const RcvMat *mag, const RcvMat *gx, const RcvMat *gy) {
   RCV_TRY(check_mat(src, "src"));
   if (src->depth != RCV_F32 || src->channels != 1) return fail(RCV_ERR_DEPTH, "Sobel: single-channel f32 only");

@@ -89,80 +89,6 @@ struct SepF32Op {
   }
 };
 
-// dense KS x KS correlation: acc = delta; acc = fmaf(k[i][j], p[y+i-r][x+j-r], acc), row-major taps
-template <int KS>
-struct Filter2dF32Op {
-  static constexpr int HV = KS / 2;
-  static constexpr int P = KS / 2;
-  static constexpr int E = 4;
-  static constexpr int NOUT = 1;
-  static constexpr int WIN = KS == 3 ? 2 : 4;
-  static constexpr int UNROLL = WIN;
-  static constexpr int XW = 4 + 2 * P;
-  float win[WIN][XW];  // previous source rows, columns -P .. 3+P
-  float k[KS * KS];
-  float delta;
-
-  __device__ __forceinline__ void init(const StripParams &p) {
-#pragma unroll
-    for (int i = 0; i < KS * KS; ++i) k[i] = p.ftaps[i];
-    delta = p.ftaps[KS * KS];
-  }
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < WIN; ++j)
-#pragma unroll
-      for (int h = 0; h < XW; ++h) win[j][h] = 0.0f;
-  }
-  __device__ __forceinline__ void widen(const uint4 &q, float (&x)[XW]) const {
-    x[P + 0] = __uint_as_float(q.x);
-    x[P + 1] = __uint_as_float(q.y);
-    x[P + 2] = __uint_as_float(q.z);
-    x[P + 3] = __uint_as_float(q.w);
-#pragma unroll
-    for (int e = 0; e < P; ++e) {
-      x[e] = __shfl_up_sync(0xffffffffu, x[P + 4 - P + e], 1);
-      x[P + 4 + e] = __shfl_down_sync(0xffffffffu, x[P + e], 1);
-    }
-  }
-  template <int J8>
-  __device__ __forceinline__ void warm(const uint4 &q) {
-    float x[XW];
-    widen(q, x);
-#pragma unroll
-    for (int c = 0; c < XW; ++c) win[J8 & (WIN - 1)][c] = x[c];
-  }
-  template <int J8, bool FAST>
-  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    float x[XW], v[4];
-    widen(q, x);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float acc = delta;
-#pragma unroll
-      for (int i = 0; i < KS - 1; ++i)
-#pragma unroll
-        for (int j = 0; j < KS; ++j) acc = fmaf(k[i * KS + j], win[(J8 + WIN * 8 - (KS - 1) + i) & (WIN - 1)][c + j], acc);
-#pragma unroll
-      for (int j = 0; j < KS; ++j) acc = fmaf(k[(KS - 1) * KS + j], x[c + j], acc);
-      v[c] = acc;
-    }
-#pragma unroll
-    for (int c = 0; c < XW; ++c) win[J8 & (WIN - 1)][c] = x[c];
-    if (!FAST && !emit) return;
-    float *o = (float *)outp[0];
-    if (FAST) {
-      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (nvalid == 16 && vec) {
-      *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (nvalid > 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c * 4 < nvalid) o[c] = v[c];
-    }
-  }
-};
-
 int launch_sepf32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *kx, int kw, const float *ky, int kh,
                           cudaStream_t s);
 int launch_filter2d_f32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
@@ -187,17 +113,10 @@ int launch_sepf32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const floa
   return launch_strip<SepF32Op<7>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 14);
 }
 
-// dense f32, single channel, 3x3 or 5x5
+// dense f32: every channel count goes through the transposed-form op of strip_f32cn.cu (3x3 / 5x5 / 7x7)
 int launch_filter2d_f32_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
                               cudaStream_t s) {
-  if (src.v.cn > 1) return launch_filter2d_f32cn_strip(c, src, dst, k, kw, kh, delta, s);
-  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_F32 || src.v.cn != 1 || kw != kh) return RCV_ERR_UNSUPPORTED;
-  if (kw != 3 && kw != 5) return RCV_ERR_UNSUPPORTED;
-  float taps[26];
-  for (int i = 0; i < kw * kh; ++i) taps[i] = k[i];
-  taps[kw * kh] = delta;
-  if (kw == 3) return launch_strip<Filter2dF32Op<3>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, 10);
-  return launch_strip<Filter2dF32Op<5>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, 26);
+  return launch_filter2d_f32cn_strip(c, src, dst, k, kw, kh, delta, s);
 }
 
 }  // namespace rcv

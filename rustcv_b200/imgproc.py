@@ -269,6 +269,20 @@ def sep_filter2d_q8_batch(srcs, dsts, kx, ky) -> None:
     F.check(F.lib.rcv_sep_filter2d_q8_batch(sa, da, n, ax.ctypes.data_as(ip), kw, ay.ctypes.data_as(ip), kh))
 
 
+def filter2d_batch(srcs, dsts, kernel, delta: float = 0.0, ngpus: int = None) -> None:
+    """Dense filter2D over a batch (one launch for a uniform device batch); ngpus: fan out over that many GPUs (0 = all)."""
+    sa, n = _arr(srcs)
+    da, m = _arr(dsts)
+    assert n == m
+    k = np.ascontiguousarray(kernel, dtype=np.float32)
+    kh, kw = k.shape
+    kp = k.ctypes.data_as(C.POINTER(C.c_float))
+    if ngpus is None:
+        F.check(F.lib.rcv_filter2d_batch(sa, da, n, kp, kw, kh, delta))
+    else:
+        F.check(F.lib.rcv_filter2d_batch_multi(sa, da, n, ngpus, kp, kw, kh, delta))
+
+
 def sep_filter2d_q8_batch_multi(srcs, dsts, ngpus: int = 0, kx=None, ky=None, kw: int = 0, kh: int = 0) -> None:
     """kx = ky = None: every GPU filters with the kw + kh taps it received from set_kernel_broadcast."""
     sa, n = _arr(srcs)

@@ -105,6 +105,8 @@ extern "C" {
     pub fn rcv_cvt_color_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, code: i32) -> c_int;
     pub fn rcv_yuyv_to_sobel_mag_batch_multi(srcs_yuyv: *const RcvMat, mags_f32: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
     pub fn rcv_yuyv_to_bgr_gaussian5_batch_multi(srcs_yuyv: *const RcvMat, dsts_bgr: *mut RcvMat, n: i32, ngpus: i32) -> c_int;
+    pub fn rcv_filter2d_batch(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, kernel: *const f32, kw: i32, kh: i32, delta: f32) -> c_int;
+    pub fn rcv_filter2d_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, kernel: *const f32, kw: i32, kh: i32, delta: f32) -> c_int;
     pub fn rcv_sep_filter2d_q8_batch_multi(srcs: *const RcvMat, dsts: *mut RcvMat, n: i32, ngpus: i32, kx: *const i32, kw: i32, ky: *const i32, kh: i32) -> c_int;
     pub fn rcv_set_kernel_broadcast(coeffs: *const f32, count: i32, root_device: i32, ngpus: i32, received: *mut f32) -> c_int;
 }

@@ -98,13 +98,10 @@ run("chain YUYV->BGR->GaussianBlur 5x5, 4K x32 [k_strip<YuyvGauss5Op>]", lambda:
 k3 = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
 
 
-def f2d_batch(srcs, dsts, k):
-    for i in range(8):
-        I.filter2d(srcs[i], dsts[i], k)
-
-
-run("filter2D 3x3, 4K BGR u8, 8 launches of 1 frame [k_strip<Filter2dU8Op<3,3>>]", lambda: f2d_batch(bgr, out3, k3), 6 * 8 * H * W)
-run("filter2D 5x5, 4K BGR u8, 8 launches of 1 frame [k_strip<Filter2dU8Op<3,5>>]", lambda: f2d_batch(bgr, out3, np.ones((5, 5), np.float32) / 25), 6 * 8 * H * W)
+run("filter2D 3x3, 4K BGR u8 x32 [k_strip<Filter2dU8Op<3,3>>]", lambda: I.filter2d_batch(bgr, out3, k3), 6 * PX)
+run("filter2D 5x5, 4K BGR u8 x32 [k_strip<Filter2dU8Op<3,5>>]", lambda: I.filter2d_batch(bgr, out3, np.ones((5, 5), np.float32) / 25), 6 * PX)
+run("filter2D 5x5, 4K BGR u8, one frame per call [k_strip<Filter2dU8Op<3,5>>]", lambda: [I.filter2d(bgr[i], out3[i], np.ones((5, 5), np.float32) / 25) for i in range(8)], 6 * 8 * H * W)
+run("filter2D 7x7, 4K BGR u8 x32, general kernel [k_filter2d<u8,7>]", lambda: I.filter2d_batch(bgr, out3, np.ones((7, 7), np.float32) / 49), 6 * PX)
 for b in (x4, yuyv, g1):
     b.free()
 # resize
@@ -146,14 +143,10 @@ run("GaussianBlur 11x11 sigma 2, 1080p BGR f32 x32, general kernel [k_sepfilter<
 I.set_option("sepf32.no_wide", 0)
 
 
-def f2df(k):
-    for i in range(8):
-        I.filter2d(f3[i], fo3[i], k)
-
-
-run("filter2D 3x3, 1080p BGR f32, 8 launches of 1 frame [k_strip<Filter2dF32CnOp<3,3>>]", lambda: f2df(k3), 24 * 8 * FH * FW)
-run("filter2D 5x5, 1080p BGR f32, 8 launches of 1 frame [k_strip<Filter2dF32CnOp<5,3>>]", lambda: f2df(np.ones((5, 5), np.float32) / 25), 24 * 8 * FH * FW)
-run("filter2D 7x7, 1080p BGR f32, 8 launches of 1 frame [k_filter2d<f32,7>]", lambda: f2df(np.ones((7, 7), np.float32) / 49), 24 * 8 * FH * FW)
+run("filter2D 3x3, 1080p BGR f32 x32 [k_strip<Filter2dF32CnOp<3,3>>]", lambda: I.filter2d_batch(f3, fo3, k3), 24 * 32 * FH * FW)
+run("filter2D 5x5, 1080p BGR f32 x32 [k_strip<Filter2dF32CnOp<5,3>>]", lambda: I.filter2d_batch(f3, fo3, np.ones((5, 5), np.float32) / 25), 24 * 32 * FH * FW)
+run("filter2D 7x7, 1080p BGR f32 x32 [k_strip<Filter2dF32CnOp<7,3>>]", lambda: I.filter2d_batch(f3, fo3, np.ones((7, 7), np.float32) / 49), 24 * 32 * FH * FW)
+run("filter2D 5x5, 1080p BGR f32, one frame per call [k_strip<Filter2dF32CnOp<5,3>>]", lambda: [I.filter2d(f3[i], fo3[i], np.ones((5, 5), np.float32) / 25) for i in range(8)], 24 * 8 * FH * FW)
 f3.free(); fo3.free()
 y8 = batch(32, FH, FW, 2, seed=6)
 mg = R.Mat.device_batch(32, FH, FW, 1, R.F32)

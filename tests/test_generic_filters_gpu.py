@@ -128,7 +128,7 @@ def test_f32_multichannel_strip_kernels(rcv, oracle, cn, ks):
         R.imgproc.gaussian_blur(s, d, (ks, ks), 1.3)
         wg = oracle.gaussian_blur(a, (ks, ks), 1.3, 1.3)
         assert (d.to_numpy().view(np.int32) == wg.view(np.int32)).all(), f"gauss cn{cn} ks{ks} {h}x{w}"
-        if (ks == 3 and cn >= 3) or (ks == 5 and cn == 3):
+        if True:  # dense filter2D: the transposed-form strip op covers every (ks, cn) here
             k = rng.normal(size=(ks, ks)).astype(np.float32)
             R.imgproc.filter2d(s, d, k, delta=-0.25)
             wf = oracle.filter2d(a, k, -0.25)
@@ -292,3 +292,92 @@ def test_round2_strip_ops_random_geometries(rcv, oracle):
         finally:
             R.imgproc.set_option("gauss.band_rows", 0)
             R.imgproc.set_option("sepf32.band_rows", 0)
+
+
+# ---- dense filter2D strip ops in transposed form (strip_f32cn.cu Filter2dF32CnOp, strip_f2d_u8.cu Filter2dU8Op) -------
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("ks", [3, 5, 7])
+def test_dense_filter2d_strip_kernels_transposed_form(rcv, oracle, cn, ks):
+    """Pending-row-sum form of the dense filters: f32 3x3 / 5x5 / 7x7 on 1..4 channels (0 ULP vs the oracle -- the
+    accumulation order must be the oracle's row-major one) and u8 3x3 / 5x5 (bit-exact); an asymmetric ramp kernel
+    catches any swap of rows, columns or direction; several strips with a ragged last one, forced band heights down to
+    one chunk (warm-up rows hoisted out of the steady loop), one launch per call, host Mats through the banded
+    pipeline, and agreement with the general kernel."""
+    R = rcv
+    rng = np.random.default_rng(ks * 100 + cn)
+    ramp = (np.arange(ks * ks, dtype=np.float32).reshape(ks, ks) - 3.0) / (ks * ks * 4)
+    for (h, w) in ((203, 517), (64, 16), (9, 40), (150, 300)):
+        shp = (h, w) if cn == 1 else (h, w, cn)
+        a = oracle.fill_f32(5000 + ks + cn, h * w * cn).reshape(shp)
+        s = R.Mat.from_numpy(a).upload()
+        d = s.like()
+        for k, delta in ((ramp, 0.0), (rng.normal(size=(ks, ks)).astype(np.float32), -0.25)):
+            for br in (0, 8, 20):
+                R.imgproc.set_option("f2d.band_rows", br)
+                try:
+                    n0 = R.imgproc.launch_count()
+                    R.imgproc.filter2d(s, d, k, delta=delta)
+                    assert R.imgproc.launch_count() - n0 == 1
+                finally:
+                    R.imgproc.set_option("f2d.band_rows", 0)
+                want = oracle.filter2d(a, k, delta)
+                assert (d.to_numpy().view(np.int32) == want.view(np.int32)).all(), f"f32 cn{cn} ks{ks} {h}x{w} band{br}"
+        if ks <= 5:
+            u = oracle.fill_u8(5100 + ks + cn, h * w * cn).reshape(shp)
+            su = R.Mat.from_numpy(u).upload()
+            du = su.like()
+            ku = (ramp * 3).astype(np.float32)
+            for br in (0, 8, 20):
+                R.imgproc.set_option("f2d.band_rows", br)
+                try:
+                    R.imgproc.filter2d(su, du, ku, delta=0.5)
+                finally:
+                    R.imgproc.set_option("f2d.band_rows", 0)
+                assert (du.to_numpy() == oracle.filter2d(u, ku, 0.5)).all(), f"u8 cn{cn} ks{ks} {h}x{w} band{br}"
+    # the general kernel agrees (same inputs, strip ops off)
+    R.imgproc.set_option("f2d.force_generic", 1)
+    try:
+        d2 = s.like()
+        R.imgproc.filter2d(s, d2, ramp, delta=0.0)
+    finally:
+        R.imgproc.set_option("f2d.force_generic", 0)
+    R.imgproc.filter2d(s, d, ramp, delta=0.0)
+    assert (d2.to_numpy().view(np.int32) == d.to_numpy().view(np.int32)).all()
+    # host Mats: the banded pinned pipeline runs the op on row windows
+    big = oracle.fill_f32(5200 + cn, 700 * 900 * cn).reshape((700, 900) if cn == 1 else (700, 900, cn))
+    hp = R.Mat.pinned(700, 900, cn, R.F32)
+    hp.data[:] = big.view(np.uint8).ravel()
+    hd = R.Mat.pinned(700, 900, cn, R.F32)
+    R.imgproc.filter2d(hp, hd, ramp, delta=0.125)
+    assert (hd.to_numpy().view(np.int32) == oracle.filter2d(big, ramp, 0.125).view(np.int32)).all(), "pinned host, banded"
+
+
+def test_filter2d_batch_entry_point(rcv, oracle):
+    """rcv_filter2d_batch: a uniform device batch is ONE launch (u8 5x5 and f32 7x7 strip ops, 13x13 general kernel);
+    host Mats go through the staging pipeline; results equal the per-frame call's."""
+    R = rcv
+    import ctypes as C
+    from rustcv_b200 import _ffi as F
+    rng = np.random.default_rng(77)
+    n, h, w = 3, 90, 400
+    for depth, cn, ks in ((R.U8, 3, 5), (R.F32, 3, 7), (R.F32, 1, 3), (R.U8, 1, 13)):
+        f32 = depth == R.F32
+        frames = [_img(oracle, 6000 + j, h, w, cn, f32) for j in range(n)]
+        src, dst = R.Mat.device_batch(n, h, w, cn, depth), R.Mat.device_batch(n, h, w, cn, depth)
+        for j in range(n):
+            hm = R.Mat.from_numpy(frames[j])
+            F.check(F.lib.rcv_mat_upload(C.byref(hm.c()), C.byref(src[j].c())))
+        k = (rng.normal(size=(ks, ks)) / ks).astype(np.float32)
+        n0 = R.imgproc.launch_count()
+        R.imgproc.filter2d_batch(src, dst, k, delta=0.25)
+        assert R.imgproc.launch_count() - n0 == 1, "one launch for the whole device batch"
+        for j in range(n):
+            want = oracle.filter2d(frames[j], k, 0.25)
+            got = dst[j].to_numpy()
+            assert (got.view(np.int32) == want.view(np.int32)).all() if f32 else (got == want).all(), f"{depth} cn{cn} ks{ks} frame {j}"
+        hs = [R.Mat.from_numpy(fr) for fr in frames]
+        hd = [R.Mat.new(h, w, cn, depth) for _ in range(n)]
+        R.imgproc.filter2d_batch(hs, hd, k, delta=0.25)
+        for j in range(n):
+            assert (hd[j].to_numpy().reshape(-1).view(np.uint8) == dst[j].to_numpy().reshape(-1).view(np.uint8)).all(), f"host batch frame {j}"
+        src.free(); dst.free()
