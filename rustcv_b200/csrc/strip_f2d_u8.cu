@@ -1,4 +1,4 @@
-// strip_f2d_u8.cu -- dense 3x3 / 5x5 filter2D on u8 (1..4 channels) in the TMA strip pipeline.
+// strip_f2d_u8.cu -- dense 3x3 / 5x5 / 7x7 filter2D on u8 (1..4 channels) in the TMA strip pipeline.
 //   acc = delta; acc = fmaf(k[i][j], (float)p[y+i-P][x+(j-P)*CN], acc) in row-major tap order;
 //   out = saturate_u8(rint(acc))           (oracle: orc_filter2d_u8; rint = round half to even)
 // Transposed form: a lane keeps, for each of its 16 samples, the running sums of the KS-1 output rows that have
@@ -25,7 +25,8 @@ struct Filter2dU8Op {
   static constexpr int HB = P * CN;          // halo bytes on each side of the lane's 16
   static constexpr int XW = 16 + 2 * HB;     // element columns -HB .. 15+HB
   static constexpr int NS = KS - 1;          // pending output rows
-  static_assert((KS == 3 || KS == 5) && HB <= 8, "3x3 / 5x5, halo within two words");
+  static constexpr int HW = (HB + 3) / 4;    // halo words on each side
+  static_assert((KS == 3 || KS == 5 || KS == 7) && HB <= 12, "3x3 / 5x5 / 7x7, halo within three words");
   float acc[NS][16];
   const StripParams *prm;  // taps: ftaps[ky * KS + kx], then delta
 
@@ -38,17 +39,15 @@ struct Filter2dU8Op {
   }
   __device__ __forceinline__ void widen(const uint4 &q, float (&x)[XW]) const {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint32_t wl[2], wr[2];  // left lane's bytes 8..15, right lane's bytes 0..7
-    wl[1] = __shfl_up_sync(0xffffffffu, w[3], 1);
-    wr[0] = __shfl_down_sync(0xffffffffu, w[0], 1);
-    wl[0] = wr[1] = 0;
-    if (HB > 4) {
-      wl[0] = __shfl_up_sync(0xffffffffu, w[2], 1);
-      wr[1] = __shfl_down_sync(0xffffffffu, w[1], 1);
+    uint32_t wl[HW], wr[HW];  // the left lane's last HW words, the right lane's first HW words
+#pragma unroll
+    for (int i = 0; i < HW; ++i) {
+      wl[i] = __shfl_up_sync(0xffffffffu, w[4 - HW + i], 1);
+      wr[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
     }
 #pragma unroll
     for (int e = 0; e < HB; ++e) {
-      const int bl = 8 - HB + e;  // byte of the left lane's last two words
+      const int bl = 4 * HW - HB + e;  // byte of the left lane's last HW words
       x[e] = byte_to_float(wl[bl >> 2], bl & 3);
       x[HB + 16 + e] = byte_to_float(wr[e >> 2], e & 3);
     }
@@ -115,23 +114,27 @@ struct Filter2dU8Op {
 
 template <int KS>
 static int launch_f2d_u8_ks(Ctx *c, const DBatch &src, const DBatch &dst, const float *taps, int ntaps, cudaStream_t s) {
+  // 7x7 keeps 6 pending rows x 16 samples: 12 warps per CTA at <= 168 registers each
+  constexpr int NW = KS == 7 ? 12 : kNW;
   switch (src.v.cn) {
-    case 1: return launch_strip<Filter2dU8Op<1, KS>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
-    case 2: return launch_strip<Filter2dU8Op<2, KS>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
-    case 3: return launch_strip<Filter2dU8Op<3, KS>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
-    case 4: return launch_strip<Filter2dU8Op<4, KS>>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
+    case 1: return launch_strip<Filter2dU8Op<1, KS>, kS, NW>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
+    case 2: return launch_strip<Filter2dU8Op<2, KS>, kS, NW>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
+    case 3: return launch_strip<Filter2dU8Op<3, KS>, kS, NW>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
+    case 4: return launch_strip<Filter2dU8Op<4, KS>, kS, NW>(c, src, &dst, 1, "f2d.band_rows", s, nullptr, nullptr, taps, ntaps);
   }
   return RCV_ERR_UNSUPPORTED;
 }
 
 int launch_filter2d_u8_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *k, int kw, int kh, float delta,
                              cudaStream_t s) {
-  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_U8 || kw != kh || (kw != 3 && kw != 5)) return RCV_ERR_UNSUPPORTED;
+  if (!strip_path_ok(src, 8, 8) || src.v.depth != RCV_U8 || kw != kh || (kw != 3 && kw != 5 && kw != 7)) return RCV_ERR_UNSUPPORTED;
   if (src.v.row_bytes() > (size_t)1 << 30) return RCV_ERR_UNSUPPORTED;
-  float taps[26];
+  float taps[50];
   for (int i = 0; i < kw * kh; ++i) taps[i] = k[i];
   taps[kw * kh] = delta;
-  return kw == 3 ? launch_f2d_u8_ks<3>(c, src, dst, taps, 10, s) : launch_f2d_u8_ks<5>(c, src, dst, taps, 26, s);
+  if (kw == 3) return launch_f2d_u8_ks<3>(c, src, dst, taps, 10, s);
+  if (kw == 5) return launch_f2d_u8_ks<5>(c, src, dst, taps, 26, s);
+  return launch_f2d_u8_ks<7>(c, src, dst, taps, 50, s);
 }
 
 }  // namespace rcv

@@ -101,7 +101,10 @@ k3 = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
 run("filter2D 3x3, 4K BGR u8 x32 [k_strip<Filter2dU8Op<3,3>>]", lambda: I.filter2d_batch(bgr, out3, k3), 6 * PX)
 run("filter2D 5x5, 4K BGR u8 x32 [k_strip<Filter2dU8Op<3,5>>]", lambda: I.filter2d_batch(bgr, out3, np.ones((5, 5), np.float32) / 25), 6 * PX)
 run("filter2D 5x5, 4K BGR u8, one frame per call [k_strip<Filter2dU8Op<3,5>>]", lambda: [I.filter2d(bgr[i], out3[i], np.ones((5, 5), np.float32) / 25) for i in range(8)], 6 * 8 * H * W)
+run("filter2D 7x7, 4K BGR u8 x32 [k_strip<Filter2dU8Op<3,7>>]", lambda: I.filter2d_batch(bgr, out3, np.ones((7, 7), np.float32) / 49), 6 * PX)
+I.set_option("f2d.force_generic", 1)
 run("filter2D 7x7, 4K BGR u8 x32, general kernel [k_filter2d<u8,7>]", lambda: I.filter2d_batch(bgr, out3, np.ones((7, 7), np.float32) / 49), 6 * PX)
+I.set_option("f2d.force_generic", 0)
 for b in (x4, yuyv, g1):
     b.free()
 # resize
