@@ -1,10 +1,14 @@
 // strip_f32wide.cu -- separable 9x9 .. 15x15 filters on f32 (gray and BGR) in the TMA strip pipeline.
 //   SepF32WideOp<KS, CN>: GaussianBlur / sepFilter2D with 9..15 taps; fmaf chains in the oracle's order
-//   (orc_sepfilter_f32: ascending taps, row pass before column pass) -- bit-identical.
-// Shape: like GaussQ8WideOp (strip_gaussq8_wide.cuh) -- 16-row chunks (2 * HV <= 14 warm-up rows, border patches one
-// chunk back), 8 warps per CTA, rows in pairs with the window of row-filtered rows shifting two slots per pair; the
-// neighbours of a row come by shuffle from up to 6 lanes away (15 taps on BGR reach 21 floats), so the op takes
-// HALO_LANES = ceil(P * CN / 4) halo lanes per side.
+//   (orc_sepfilter_f32: ascending taps from 0.0f, row pass before column pass) -- bit-identical.
+// Shape: 16-row chunks (2 * HV <= 14 warm-up rows, border patches one chunk back); the neighbours of a row come by
+// shuffle from up to 6 lanes away (15 taps on BGR reach 21 floats), so the op takes HALO_LANES = ceil(P * CN / 4) halo
+// lanes per side.  The column pass runs in TRANSPOSED form (second session of round 2, see Filter2dF32CnOp): a lane
+// keeps the KS-1 pending column sums of its 4 floats; a row-filtered row h extends each (acc_i = fmaf(ky[KS-2-i],
+// h, acc_{i+1})), completes the oldest and starts a new one (fmaf(ky[0], h, 0.0f)) -- the oracle's ascending order.
+// Against the first version (a window of KS-1 row-filtered rows shifted two slots per row pair): no (KS-2) x 4
+// register moves per pair, the 2 x KS taps are uniform-register operands instead of 30 registers, so BGR 11..15 taps
+// fit 12 warps per CTA instead of 8, and the loop is unpredicated.
 #include "strip_f32_gather.cuh"
 
 namespace rcv {
@@ -18,64 +22,45 @@ struct SepF32WideOp {
   static constexpr int HALO_LANES = (REACH + 3) / 4;
   static constexpr int NOUT = 1;
   static constexpr int UNROLL = 2;
-  static constexpr bool SINGLE_PATH = true;
   static constexpr int BAND_ROWS = 7 * 16 - 2 * HV;
+  static constexpr int NS = KS - 1;  // pending output rows
   static_assert(KS >= 9 && KS <= 15 && (KS & 1), "kernel size");
-  float win[KS][4];  // slots 0..KS-2: previous row-filtered rows, oldest first (at a pair's first row); slot KS-1: that first row
-  float kx[KS], ky[KS];
+  float acc[NS][4];
+  const StripParams *prm;  // ftaps: kx[0..KS), ky[0..KS)
 
-  __device__ __forceinline__ void init(const StripParams &p) {
-#pragma unroll
-    for (int i = 0; i < KS; ++i) {
-      kx[i] = p.ftaps[i];
-      ky[i] = p.ftaps[KS + i];
-    }
-  }
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < KS; ++j)
-#pragma unroll
-      for (int h = 0; h < 4; ++h) win[j][h] = 0.0f;
-  }
-  template <int J8>
-  __device__ __forceinline__ void warm(const uint4 &) {}  // SINGLE_PATH: never called
+  __device__ __forceinline__ void init(const StripParams &p) { prm = &p; }
+  __device__ __forceinline__ void reset() {}  // 2*HV warm-up rows rebuild every pending sum
 
-  template <int J8, bool FAST>
-  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
-    constexpr int U = J8 & 1;
-    float x[4 + 2 * REACH], h[4];
-    gather_row<REACH>(q, x);  // shuffles: executed by the whole warp whether or not the row emits
+  // row pass of this lane's 4 floats, then the column sums move up one slot; returns the completed row
+  __device__ __forceinline__ void step(const uint4 &q, float (&v)[4]) {
+    float x[4 + 2 * REACH];
+    gather_row<REACH>(q, x);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float acc = 0.0f;
+      float h = 0.0f;
 #pragma unroll
-      for (int j = 0; j < KS; ++j) acc = fmaf(kx[j], x[REACH + c + (j - P) * CN], acc);
-      h[c] = acc;
+      for (int j = 0; j < KS; ++j) h = fmaf(prm->ftaps[j], x[REACH + c + (j - P) * CN], h);
+      v[c] = fmaf(prm->ftaps[KS + KS - 1], h, acc[0][c]);  // the newest row is the last tap of the oldest pending sum
+#pragma unroll
+      for (int i = 0; i < NS - 1; ++i) acc[i][c] = fmaf(prm->ftaps[KS + KS - 2 - i], h, acc[i + 1][c]);
+      acc[NS - 1][c] = fmaf(prm->ftaps[KS], h, 0.0f);
     }
-    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (emit) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int i = 0; i < KS - 1; ++i) acc = fmaf(ky[i], win[i + U][c], acc);  // oldest row first
-        v[c] = fmaf(ky[KS - 1], h[c], acc);
-      }
-    }
-    if (U == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) win[KS - 1][c] = h[c];
-    } else {
-#pragma unroll
-      for (int i = 0; i < KS - 2; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) win[i][c] = win[i + 2][c];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) win[KS - 2][c] = h[c];
-    }
-    if (!emit) return;
+  }
+  // warm-up rows run the full update: whatever the sums held before is pushed out within KS-1 rows
+  template <int J8>
+  __device__ __forceinline__ void warm(const uint4 &q) {
+    float v[4];
+    step(q, v);
+  }
+  template <int J8, bool FAST>
+  __device__ __forceinline__ void feed(const uint4 &q, bool emit, uint8_t *const *outp, int nvalid, bool vec) {
+    float v[4];
+    step(q, v);
+    if (!FAST && !emit) return;
     float *o = (float *)outp[0];
-    if (nvalid == 16 && vec) {
+    if (FAST) {
+      if (nvalid == 16) *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (nvalid == 16 && vec) {
       *(float4 *)o = make_float4(v[0], v[1], v[2], v[3]);
     } else if (nvalid > 0) {
 #pragma unroll
@@ -87,12 +72,9 @@ struct SepF32WideOp {
 
 template <int KS>
 static int launch_sepf32wide_ks(Ctx *c, const DBatch &src, const DBatch &dst, const float *taps, cudaStream_t s) {
-  // gray: under 170 registers per thread, so 12 warps fit (2 stages of 16 rows per warp = 192 KB per CTA)
+  // 12 warps x 2 stages of 16 rows = 192 KB per CTA; every instance stays under 168 registers per thread
   if (src.v.cn == 1) return launch_strip<SepF32WideOp<KS, 1>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
-  if (src.v.cn == 3) {
-    if constexpr (KS <= 9) return launch_strip<SepF32WideOp<KS, 3>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
-    else return launch_strip<SepF32WideOp<KS, 3>, kS, 8, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
-  }
+  if (src.v.cn == 3) return launch_strip<SepF32WideOp<KS, 3>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
   return RCV_ERR_UNSUPPORTED;
 }
 
