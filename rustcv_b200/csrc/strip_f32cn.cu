@@ -1,6 +1,6 @@
 // strip_f32cn.cu -- multi-channel f32 ops of the TMA strip pipeline (see strip_pipeline.cuh):
 //   SepF32CnOp<KS, CN>      separable KS x KS filter (GaussianBlur / sepFilter2D on f32 BGR / BGRA / 2-channel), KS = 3, 5, 7
-//   Filter2dF32CnOp<KS, CN> dense KS x KS correlation, KS = 3, 5
+//   Filter2dF32CnOp<KS, CN> dense KS x KS correlation, KS = 3, 5, 7, CN = 1..4 (transposed form: pending row sums)
 // The single-channel ops (strip_f32.cu) take their row neighbours from the adjacent lane; with CN interleaved
 // channels tap j of a pixel lies (j - P) * CN floats away, up to 9 (3 lanes) for a 7-tap filter on BGR, so these
 // ops give up more than one halo lane per side (Op::HALO_LANES) and fetch each neighbour float with one shuffle
