@@ -157,8 +157,6 @@ struct Filter2dF32CnOp {
   }
 };
 
-int launch_sepf32_t7_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *taps, cudaStream_t s);
-
 template <int KS>
 static int launch_sepf32cn_ks(Ctx *c, const DBatch &src, const DBatch &dst, const float *taps, cudaStream_t s) {
   switch (src.v.cn) {
@@ -181,7 +179,6 @@ int launch_sepf32cn_strip(Ctx *c, const DBatch &src, const DBatch &dst, const fl
   }
   if (kw == 3) return launch_sepf32cn_ks<3>(c, src, dst, taps, s);
   if (kw == 5) return launch_sepf32cn_ks<5>(c, src, dst, taps, s);
-  if (opt_get("sepf32.windowed7", 0) == 0) return launch_sepf32_t7_strip(c, src, dst, taps, s);
   return launch_sepf32cn_ks<7>(c, src, dst, taps, s);
 }
 

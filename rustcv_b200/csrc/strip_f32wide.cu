@@ -22,9 +22,9 @@ struct SepF32WideOp {
   static constexpr int HALO_LANES = (REACH + 3) / 4;
   static constexpr int NOUT = 1;
   static constexpr int UNROLL = 2;
-  static constexpr int BAND_ROWS = KS >= 9 ? 7 * 16 - 2 * HV : 8 * 8 - 2 * HV;  // warm-up rows cost a full update here
+  static constexpr int BAND_ROWS = 7 * 16 - 2 * HV;
   static constexpr int NS = KS - 1;  // pending output rows
-  static_assert(KS >= 7 && KS <= 15 && (KS & 1), "kernel size");
+  static_assert(KS >= 9 && KS <= 15 && (KS & 1), "kernel size");  // 7 taps: measured slower than SepF32CnOp's 8-row window (0.79 vs 0.83)
   float acc[NS][4];
   const StripParams *prm;  // ftaps: kx[0..KS), ky[0..KS)
 
@@ -75,16 +75,6 @@ static int launch_sepf32wide_ks(Ctx *c, const DBatch &src, const DBatch &dst, co
   // 12 warps x 2 stages of 16 rows = 192 KB per CTA; every instance stays under 168 registers per thread
   if (src.v.cn == 1) return launch_strip<SepF32WideOp<KS, 1>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
   if (src.v.cn == 3) return launch_strip<SepF32WideOp<KS, 3>, 2, 12, 16>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 2 * KS);
-  return RCV_ERR_UNSUPPORTED;
-}
-
-// 7 taps on 2..4 channels (8-row chunks, 16 warps): the transposed column pass instead of SepF32CnOp's 8-row window
-int launch_sepf32_t7_strip(Ctx *c, const DBatch &src, const DBatch &dst, const float *taps, cudaStream_t s) {
-  switch (src.v.cn) {
-    case 2: return launch_strip<SepF32WideOp<7, 2>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 14);
-    case 3: return launch_strip<SepF32WideOp<7, 3>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 14);
-    case 4: return launch_strip<SepF32WideOp<7, 4>>(c, src, &dst, 1, "sepf32.band_rows", s, nullptr, nullptr, taps, 14);
-  }
   return RCV_ERR_UNSUPPORTED;
 }
 
