@@ -578,7 +578,9 @@ __device__ __forceinline__ void warp_pixel(const WarpTileArgs &t, uint32_t tile,
   }
   const int cxb = ix * E - bx0, cy = iy - by0;  // byte offset of tap (0,0) inside the box
   if (!INTERIOR) inbox = cxb >= 0 && cxb + 2 * E <= rowb && (unsigned)cy < (unsigned)(t.bh - 1);
-  const uint32_t p = tile + (uint32_t)(cy * rowb + cxb);
+  // interior tiles: `tile` arrives with the box origin folded in (tile - by0 * rowb - bx0), so the tap address is one
+  // multiply-add and one shift-add instead of four operations per pixel
+  const uint32_t p = INTERIOR ? tile + (uint32_t)(iy * rowb) + (uint32_t)(ix * E) : tile + (uint32_t)(cy * rowb + cxb);
 #pragma unroll
   for (int ch = 0; ch < CN; ++ch) {
     float p00, p01, p10, p11;
@@ -675,15 +677,26 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp_tile(const __grid_constan
   const bool full = tx0 + kWarpTW <= a.dcols && ty0 + TH <= a.drows;
   mbar_wait(barp, 0);
   if (interior && full) {
+    const uint32_t tile0 = tile - (uint32_t)(by0 * (t.bw * 4)) - (uint32_t)bx0;  // box origin folded into the base
+    // the output address as ONE global-space register pair, advanced by one 64-bit add per pixel (the compiler's own
+    // form was a uniform base + a running offset = two 64-bit adds, or a 64-bit multiply-add from the tile's first row)
+    unsigned long long o8 = (unsigned long long)__cvta_generic_to_global(drow);
+    asm volatile("" : "+l"(o8));
+    const unsigned long long step4 = 4ull * a.dstep;
 #pragma unroll
     for (int k = 0; k < TH / 4; ++k) {
       float bx, by;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bx), "=f"(by) : "r"(rowtab + (ly0 + 4 * k) * 8));
       T v[CN];
-      warp_pixel<T, CN, true>(t, tile, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src, v);
-      T *o = (T *)(drow + (size_t)(4 * k) * a.dstep);
+      warp_pixel<T, CN, true>(t, tile0, bx0, by0, fmaf(a.m0, xf, bx), fmaf(a.m3, xf, by), src, v);
 #pragma unroll
-      for (int ch = 0; ch < CN; ++ch) o[ch] = v[ch];
+      for (int ch = 0; ch < CN; ++ch) {
+        if (sizeof(T) == 4)
+          asm volatile("st.global.f32 [%0], %1;" ::"l"(o8 + ch * 4), "f"((float)v[ch]) : "memory");
+        else
+          asm volatile("st.global.u8 [%0], %1;" ::"l"(o8 + ch), "r"((uint32_t)v[ch]) : "memory");
+      }
+      o8 += step4;
     }
   } else {
 #pragma unroll 2
