@@ -162,6 +162,56 @@ __global__ void __launch_bounds__(128) k_resize4x_u8c3(const ResizeArgs a) {
 // adjacent pixels, i.e. 2*CN contiguous bytes: here they are fetched as the aligned 32-bit words that cover them
 // and moved into place with funnel shifts (6 word loads per BGR pixel instead of 12 byte loads), and a thread
 // makes 4 destination pixels so that its output leaves as words.  Same fixed-point arithmetic.
+// One destination pixel of k_resize_u8w.  SAFE: the words wi .. wi+2 of both rows exist (every pixel but the last
+// few of a row), so the three loads of a row share one 64-bit address with immediate offsets; otherwise the word index
+// is clamped to the row's last word per load (a 64-bit address computation each).
+template <int CN, bool SAFE>
+__device__ __forceinline__ void resize_px_u8w(const uint32_t *s0, const uint32_t *s1, const int2 e, int last_word, uint32_t b0s,
+                                              uint32_t b1s, uint32_t *ob) {
+  const int x0 = e.x;
+  const uint32_t a0 = (uint32_t)e.y & 0xFFFFu, a1 = (uint32_t)e.y >> 16;
+  const int o = x0 * CN, wi = o >> 2, sh = (o & 3) * 8;
+  uint32_t p0[2][CN], p1[2][CN];  // [row][channel]: tap (x0) and tap (x1)
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const uint32_t *row = (rr ? s1 : s0) + wi;
+    // the two taps are bytes o .. o + 2*CN - 1: one to three aligned words, shifted into place
+    const uint32_t w0 = __ldg(row);
+    uint32_t lo, hi = 0;
+    if (CN == 4) {
+      lo = w0;  // o is a multiple of 4: the two pixels are the two words
+      hi = SAFE ? __ldg(row + 1) : __ldg(row + min(1, last_word - wi));
+    } else if (CN == 3) {
+      const uint32_t w1 = SAFE ? __ldg(row + 1) : __ldg(row + min(1, last_word - wi));
+      uint32_t w2 = 0;  // a third word only when the first tap starts at byte 3 of its word
+      if (sh == 24) w2 = SAFE ? __ldg(row + 2) : __ldg(row + min(2, last_word - wi));
+      lo = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
+      hi = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
+    } else {
+      uint32_t w1 = 0;  // gray / 2 channels: the second word only when the taps straddle a word boundary
+      if (sh + 16 * CN > 32) w1 = SAFE ? __ldg(row + 1) : __ldg(row + min(1, last_word - wi));
+      lo = __funnelshift_r(w0, w1, sh);
+    }
+    // one PRMT per tap byte (shift + mask were two ALU-pipe operations each, and that pipe is this kernel's limit:
+    // profiles/r2_resize_general_ncu_before.txt, ALU 85 % busy).  A column clamped at the right edge has
+    // a0 = 2048, a1 = 0 in the compact table, so its second tap (whatever lies there) contributes nothing.
+#pragma unroll
+    for (int ch = 0; ch < CN; ++ch) {
+      p0[rr][ch] = __byte_perm(lo, 0, 0x4440 | ch);
+      const int k = CN + ch;  // byte index of the second tap
+      p1[rr][ch] = k < 4 ? __byte_perm(lo, 0, 0x4440 | k) : __byte_perm(hi, 0, 0x4440 | (k - 4));
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < CN; ++ch) {
+    const uint32_t S0 = p0[0][ch] * a0 + p1[0][ch] * a1;
+    const uint32_t S1 = p0[1][ch] * a0 + p1[1][ch] * a1;
+    // (b * (S >> 4)) >> 16 as the high word of (b << 16) * (S >> 4): one multiply, no shift
+    const uint32_t v = (__umulhi(S0 >> 4, b0s) + __umulhi(S1 >> 4, b1s) + 2u) >> 2;
+    ob[ch] = min(v, 255u);  // v <= 255 whenever the weights sum to 2048; kept for the oracle's saturate
+  }
+}
+
 template <int CN>
 __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
   static_assert(CN >= 1 && CN <= 4, "1..4 interleaved u8 channels");
@@ -178,54 +228,17 @@ __global__ void __launch_bounds__(128) k_resize_u8w(const ResizeArgs a) {
   const int last_word = (a.scols * CN - 1) >> 2;  // the last word holding row bytes
   const uint32_t b0s = (uint32_t)r.b0 << 16, b1s = (uint32_t)r.b1 << 16;
   uint32_t ob[4 * CN];                            // output bytes of the 4 pixels
+  // the group's four 8-byte table entries (x0, a0 | a1 << 16) as two 128-bit loads: the table is padded with copies of
+  // its last entry, so a ragged last group recomputes its last pixel (not stored).  (The 24-byte ResizeCol cost a warp
+  // 12 L1 wavefronts per pixel column.)
+  const int4 t0 = __ldg((const int4 *)(a.cols8 + dx0)), t1 = __ldg((const int4 *)(a.cols8 + dx0) + 1);
+  const int2 e[4] = {make_int2(t0.x, t0.y), make_int2(t0.z, t0.w), make_int2(t1.x, t1.y), make_int2(t1.z, t1.w)};
+  if (((e[3].x * CN) >> 2) + 2 <= last_word) {  // x0 grows with dx: the last pixel's words exist, so all do
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int dx = min(dx0 + q, a.dcols - 1);  // a ragged last group recomputes its last pixel (not stored)
-    // one 8-byte table entry per destination column (the 24-byte ResizeCol cost a warp 12 L1 wavefronts per pixel
-    // column, this costs 2)
-    const int2 e = __ldg(a.cols8 + dx);
-    const int x0 = e.x;
-    const int2 aa = make_int2(e.y & 0xFFFF, (int)((unsigned)e.y >> 16));
-    const int o = x0 * CN, wi = o >> 2, sh = (o & 3) * 8;
-    uint32_t p0[2][CN], p1[2][CN];  // [row][channel]: tap (x0) and tap (x1)
+    for (int q = 0; q < 4; ++q) resize_px_u8w<CN, true>(s0, s1, e[q], last_word, b0s, b1s, ob + q * CN);
+  } else {
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const uint32_t *row = rr ? s1 : s0;
-      // the two taps are bytes o .. o + 2*CN - 1: one to three aligned words, shifted into place
-      const uint32_t w0 = __ldg(row + wi);
-      uint32_t lo, hi = 0;
-      if (CN == 4) {
-        lo = w0;  // o is a multiple of 4: the two pixels are the two words
-        hi = __ldg(row + min(wi + 1, last_word));
-      } else if (CN == 3) {
-        const uint32_t w1 = __ldg(row + min(wi + 1, last_word));
-        uint32_t w2 = 0;  // a third word only when the first tap starts at byte 3 of its word
-        if (sh == 24) w2 = __ldg(row + min(wi + 2, last_word));
-        lo = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
-        hi = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
-      } else {
-        uint32_t w1 = 0;  // gray / 2 channels: the second word only when the taps straddle a word boundary
-        if (sh + 16 * CN > 32) w1 = __ldg(row + min(wi + 1, last_word));
-        lo = __funnelshift_r(w0, w1, sh);
-      }
-      // one PRMT per tap byte (shift + mask were two ALU-pipe operations each, and that pipe is this kernel's limit:
-      // profiles/r2_resize_general_ncu_before.txt, ALU 85 % busy).  A column clamped at the right edge has
-      // a0 = 2048, a1 = 0 in the compact table, so its second tap (whatever lies there) contributes nothing.
-#pragma unroll
-      for (int ch = 0; ch < CN; ++ch) {
-        p0[rr][ch] = __byte_perm(lo, 0, 0x4440 | ch);
-        const int k = CN + ch;  // byte index of the second tap
-        p1[rr][ch] = k < 4 ? __byte_perm(lo, 0, 0x4440 | k) : __byte_perm(hi, 0, 0x4440 | (k - 4));
-      }
-    }
-#pragma unroll
-    for (int ch = 0; ch < CN; ++ch) {
-      const uint32_t S0 = p0[0][ch] * (uint32_t)aa.x + p1[0][ch] * (uint32_t)aa.y;
-      const uint32_t S1 = p0[1][ch] * (uint32_t)aa.x + p1[1][ch] * (uint32_t)aa.y;
-      // (b * (S >> 4)) >> 16 as the high word of (b << 16) * (S >> 4): one multiply, no shift
-      const uint32_t v = (__umulhi(S0 >> 4, b0s) + __umulhi(S1 >> 4, b1s) + 2u) >> 2;
-      ob[q * CN + ch] = min(v, 255u);  // v <= 255 whenever the weights sum to 2048; kept for the oracle's saturate
-    }
+    for (int q = 0; q < 4; ++q) resize_px_u8w<CN, false>(s0, s1, e[q], last_word, b0s, b1s, ob + q * CN);
   }
   uint8_t *d = a.dst + (size_t)blockIdx.z * a.dfs + (size_t)dy * a.dstep + (size_t)dx0 * CN;
   if (dx0 + 4 <= a.dcols) {
@@ -401,7 +414,7 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
   // the per-column / per-row tables depend on the geometry only: rebuilt and uploaded when it changes
   void *dcols = nullptr, *drows = nullptr;
   const size_t cols8_off = ((size_t)dst.v.cols * sizeof(ResizeCol) + 15) & ~(size_t)15;
-  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, cols8_off + (size_t)dst.v.cols * sizeof(int2), &dcols));
+  RCV_TRY(ctx_scratch(c, SCR_TABLE_X, cols8_off + ((size_t)dst.v.cols + 3) * sizeof(int2), &dcols));
   RCV_TRY(ctx_scratch(c, SCR_TABLE_Y, (size_t)dst.v.rows * sizeof(ResizeRow), &drows));
   const int key[4] = {src.v.rows, src.v.cols, dst.v.rows, dst.v.cols};
   if (memcmp(key, c->resize_key, sizeof(key)) != 0) {
@@ -409,10 +422,11 @@ int launch_resize(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream_t s) 
     std::vector<ResizeRow> rows;
     resize_tables(src.v.rows, src.v.cols, dst.v.rows, dst.v.cols, cols, rows);
     RCV_CUDA(cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(ResizeCol), cudaMemcpyHostToDevice, s));
-    std::vector<int2> cols8(cols.size());
+    std::vector<int2> cols8(cols.size() + 3);  // + 3 copies of the last entry: a group of 4 is read whole
     for (size_t i = 0; i < cols.size(); ++i)
       cols8[i] = cols[i].x1 == cols[i].x0 ? make_int2(cols[i].x0, cols[i].a0 + cols[i].a1)  // clamped: one tap takes both weights
                                           : make_int2(cols[i].x0, cols[i].a0 | (cols[i].a1 << 16));
+    for (size_t i = cols.size(); i < cols8.size(); ++i) cols8[i] = cols8[cols.size() - 1];
     RCV_CUDA(cudaMemcpyAsync((uint8_t *)dcols + cols8_off, cols8.data(), cols8.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     RCV_CUDA(cudaMemcpyAsync(drows, rows.data(), rows.size() * sizeof(ResizeRow), cudaMemcpyHostToDevice, s));
     // the vectors die at return: do not depend on how the driver stages pageable sources
