@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_strip -s 4 -c 1 -f -o gpurun_out/prof_gauss5_r2f python bench.py $BARGS > gpurun_out/r2f_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control base --import-source on -k regex:k_strip -s 4 -c 1 -f -o gpurun_out/prof_gauss5_r2f_baseclk python bench.py $BARGS > gpurun_out/r2f_ncu_full_base.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_resize_u8w -s 3 -c 1 -f -o gpurun_out/prof_resize_r2f env SECONDS_PER_CASE=0.01 python scripts/bench_all_kernels.py "1600x900" > gpurun_out/r2f_ncu_resize.log 2>&1
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_generic_filters_gpu.py -m gpu -q -x -p no:cacheprovider -k "gauss or resize or yuyv_to or chain or sobel or sep or band_seams or tiny" > gpurun_out/r2f_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r2f_sanitizer_memcheck.txt
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_generic_filters_gpu.py -m gpu -q -x -p no:cacheprovider -k "gauss or resize or yuyv_to or chain or sobel or sep or band_seams or tiny or dense or filter2d or warp" > gpurun_out/r2f_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r2f_sanitizer_memcheck.txt
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_generic_filters_gpu.py -m gpu -q -x -p no:cacheprovider -k "gaussian5_binomial or band_seams or yuyv_to or any_sigma or gaussq or sobel" > gpurun_out/r2f_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"; tail -3 gpurun_out/r2f_sanitizer_racecheck.txt
 python - <<'PY'
 import json
