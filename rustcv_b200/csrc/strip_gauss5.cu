@@ -142,7 +142,4 @@ int launch_gauss5_strip(Ctx *c, const DBatch &src, const DBatch &dst, cudaStream
   return RCV_ERR_UNSUPPORTED;
 }
 
-// KS x KS GaussianBlur with arbitrary symmetric non-negative Q8 taps (sum 256), KS in {3, 5, 7}.
-// kx/ky hold KS taps each.  RCV_ERR_UNSUPPORTED -> the caller uses the generic kernel.
-
 }  // namespace rcv

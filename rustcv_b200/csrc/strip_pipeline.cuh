@@ -2,8 +2,10 @@
 //   k_strip<Gauss5Op<CN>>      5x5 binomial GaussianBlur on u8 (the BASELINE.json metric kernel)   strip_gauss5.cu
 //   k_strip<Gauss3Op<CN>>      3x3 binomial GaussianBlur on u8                                      strip_gauss3.cu
 //   k_strip<GaussQ8Op<CN,KS>>  any-sigma 3x3 / 5x5 / 7x7 GaussianBlur on u8                          strip_gaussq8*.cu
+//   k_strip<GaussQ8WideOp<CN,KS>>  any-sigma 9x9 .. 15x15 GaussianBlur on u8                          strip_gaussq8_wide.cuh
 //   k_strip<Sobel3Op<ALL>>     Sobel 3x3 + gradient magnitude on f32                                strip_sobel.cu
-//   k_strip<SepF32Op / Filter2dF32Op / Filter2dU8Op>   separable and dense filters                  strip_f32.cu, strip_f2d_u8.cu
+//   k_strip<SepF32Op / SepF32CnOp / SepF32WideOp>      separable filters on f32, 3 .. 15 taps       strip_f32*.cu
+//   k_strip<Filter2dF32CnOp / Filter2dU8Op>            dense 3x3 / 5x5 / 7x7 filters (transposed form) strip_f32cn.cu, strip_f2d_u8.cu
 //   k_strip<YuyvSobelOp>, k_strip<YuyvGauss5Op>        fused decode -> process chains               strip_yuyv_*.cu
 //
 // The reference has no such ops (rustcv/src/imgproc/mod.rs:1-4 is drawing only); the
@@ -19,9 +21,10 @@
 //     warp waits on the mbarrier, reads its rows with conflict-free 128-bit LDS and
 //     refills the stage.  512 B = 32 lanes x 16 B; lanes 0 and 31 are halo lanes, so
 //     the strip's 480 output bytes are written by lanes 1..30 as 128-bit STG.
-//   * The warp marches DOWN the strip keeping the last 2*HV rows in registers, so every
-//     source row is read from shared memory exactly once and the vertical pass needs no
-//     re-reads; the horizontal pass takes its neighbours by warp shuffle.
+//   * The warp marches DOWN the strip keeping either the last 2*HV rows or -- transposed form -- the partial
+//     sums of the 2*HV outputs still open in registers, so every source row is read from shared memory
+//     exactly once and the vertical pass needs no re-reads; the horizontal pass takes its neighbours by
+//     warp shuffle.
 //   * u8 arithmetic is SIMD-in-register: two samples per 32-bit register as 16-bit lanes
 //     (vertical sums <= 4088, final sums <= 65408 fit exactly), PRMT for the stride-CN
 //     byte gathers.
