@@ -355,3 +355,58 @@ def test_gray_pair_byte_split_identity_exhaustive():
     B = 151 * b + 35 * g + 70 * r
     assert A.max() <= 32385 and B.max() <= 65280 and (A + (B >> 8) + 64).max() < 65536
     assert (((3735 * b + 19235 * g + 9798 * r + 16384) >> 15) == ((A + (B >> 8) + 64) >> 7)).all()
+
+
+def test_transposed_form_recurrences_equal_the_windowed_sums():
+    """The strip ops keep partial sums instead of a window of rows (Gauss5Op, GaussQ8Op, the dense filter ops):
+    s4 = x_n, s3 = x_{n-1} + 4 x_n, s2 = x_{n-2} + 4 x_{n-1} + 6 x_n, s1 = x_{n-3} + 4 x_{n-2} + 6 x_{n-1} + 4 x_n and
+    V = s1 + x_{n+1}; in general out = s_0 + K[KS-1] x, s_i = s_{i+1} + K[KS-2-i] x, s_{KS-2} = K[0] x.  Checked in
+    integers against the direct vertical sums for the binomial 5 taps and random symmetric Q8 taps of 3..15, whatever
+    the state held before the first KS-1 rows (the ops never reset it)."""
+    rng = np.random.default_rng(11)
+    for ks in (3, 5, 7, 9, 15):
+        taps = [np.array([1, 4, 6, 4, 1])] if ks == 5 else []
+        for _ in range(3):
+            h = rng.integers(0, 60, size=ks // 2 + 1)
+            k = np.concatenate([h, h[-2::-1]])
+            taps.append(k)
+        for K in taps:
+            rows = rng.integers(0, 256, size=(40, 16)).astype(np.int64)
+            state = [rng.integers(0, 1000, size=16).astype(np.int64) for _ in range(ks - 1)]  # garbage on purpose
+            outs = []
+            for x in rows:
+                outs.append(state[0] + K[ks - 1] * x)
+                for i in range(ks - 2):
+                    state[i] = state[i + 1] + K[ks - 2 - i] * x
+                state[ks - 2] = K[0] * x
+            for n in range(ks - 1, len(rows)):
+                want = sum(K[i] * rows[n - (ks - 1) + i] for i in range(ks))
+                assert (outs[n] == want).all(), (ks, n)
+
+
+def test_dense_transposed_form_keeps_the_row_major_f32_order():
+    """Filter2dF32CnOp / Filter2dU8Op: every pending output row is a running fmaf chain that meets its kernel rows in
+    ky order and, inside a row, its taps in kx order -- the oracle's row-major order, so the f32 result is bit-identical.
+    The two sides use the same fma emulation: what is compared is the ORDER of the chain, not the rounding model."""
+    rng = np.random.default_rng(12)
+
+    def fmaf(a, b, c):
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    ks = 5
+    k = rng.normal(size=(ks, ks)).astype(np.float32)
+    img = rng.random(size=(12, 12)).astype(np.float32)
+    delta = np.float32(0.25)
+    # oracle order for the one output whose window is img[0:5, 3:8]
+    acc = delta
+    for i in range(ks):
+        for j in range(ks):
+            acc = fmaf(k[i, j], img[i, 3 + j], acc)
+    # transposed: the pending sum of that output row as the rows 0..4 arrive
+    pend = None
+    for r in range(ks):
+        s = delta if r == 0 else pend
+        for j in range(ks):
+            s = fmaf(k[r, j], img[r, 3 + j], s)
+        pend = s
+    assert pend.view(np.int32) == acc.view(np.int32)
