@@ -29,18 +29,19 @@ struct GaussQ8Op {
   static constexpr bool HOIST_WARM = true;
   // warm-up rows cost a full horizontal pass here: taller bands than the default 5 chunks for the larger kernels
   // (measured, 5x5 on 32 x 4K BGR: 0.573 of the roofline at 36 rows, 0.585 at 60, 0.583 at 76, 0.573 at 116)
-  static constexpr int BAND_ROWS = KS == 3 ? 5 * 8 - 2 * HV : 8 * 8 - 2 * HV;
+  static constexpr int BAND_ROWS = KS == 3 ? 5 * 8 - 2 * HV : KS <= 7 ? 8 * 8 - 2 * HV : 7 * 16 - 2 * HV;
   static constexpr int EXT = (HV * CN + 3) / 4;  // neighbour words needed on each side
-  static_assert(KS == 3 || KS == 5 || KS == 7, "kernel size");
-  static_assert(EXT <= 3, "taps beyond three words");
+  static constexpr int HALO_LANES = 1;           // every tap within the adjacent lanes (9 / 11 taps: CN * HV <= 16 bytes)
+  static_assert(KS == 3 || KS == 5 || KS == 7 || KS == 9 || KS == 11, "kernel size");
+  static_assert(EXT <= 4 && HV * CN <= 16, "taps beyond the adjacent lane");
   uint32_t sa[NS][8], sb[NS][8];  // partial sums of the low / high 16-bit lane's sample of register pair h
   uint32_t kx[HV + 1], ky[HV + 1];
 
   __device__ __forceinline__ void init(const StripParams &p) {
 #pragma unroll
-    for (int i = 0; i <= HV; ++i) {
-      kx[i] = p.taps_x[i];
-      ky[i] = p.taps_y[i];
+    for (int i = 0; i <= HV; ++i) {  // 9 / 11 taps arrive in the wide-tap slots (x: wtaps[0..7], y: wtaps[8..15])
+      kx[i] = KS <= 7 ? p.taps_x[i & 3] : p.wtaps[i];
+      ky[i] = KS <= 7 ? p.taps_y[i & 3] : p.wtaps[8 + i];
     }
   }
   __device__ __forceinline__ void reset() {}  // the 2*HV warm-up rows overwrite every partial sum

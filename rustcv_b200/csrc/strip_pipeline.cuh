@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
           if (c == 0) {  // the band's first 2*HV rows fill the window, straight-line; the steady loop takes over after them
             const uint32_t rowaddr = tile + lane * kLaneBytes;
 #pragma unroll
+            static_assert(2 * HV <= R && 2 * HV <= 14, "the window-filling rows lie in the band's first chunk");
             for (int j = 0; j < 2 * HV; ++j) {
               const uint4 q = lds128(rowaddr + j * kTileBytes);
               if (j == 0) op.template warm<0>(q);
@@ -339,12 +340,19 @@ __global__ void __launch_bounds__(NW * 32, 1) k_strip(const __grid_constant__ CU
               if (j == 5) op.template warm<5>(q);
               if (j == 6) op.template warm<6>(q);
               if (j == 7) op.template warm<7>(q);
+              if (j == 8) op.template warm<8>(q);  // 16-row chunks: ops with more than 4 halo rows
+              if (j == 9) op.template warm<9>(q);
+              if (j == 10) op.template warm<10>(q);
+              if (j == 11) op.template warm<11>(q);
+              if (j == 12) op.template warm<12>(q);
+              if (j == 13) op.template warm<13>(q);
             }
             g0 = 2 * HV / U;
           }
         }
         if constexpr (OpHoistWarm<Op>::value && (2 * HV) % U != 0) {
           if (c == 0) {  // the band's first chunk, straight-line: 2*HV rows fill the window, the rest emit
+            static_assert(R == 8, "the straight-line first chunk dispatches rows 0..7");
             const uint32_t rowaddr = tile + lane * kLaneBytes;
 #pragma unroll
             for (int j = 0; j < R; ++j) {

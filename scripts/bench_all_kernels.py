@@ -79,7 +79,12 @@ run("GaussianBlur 3x3 sigma 0, 4K BGR u8 x32 [k_strip<Gauss3Op<3>>]", lambda: I.
 for ks, sg in ((3, 0.8), (5, 1.0), (7, 1.5)):
     run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32 [k_strip<GaussQ8Op<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
 for ks, sg in ((9, 1.5), (11, 2.0), (13, 2.0), (15, 2.5)):
-    run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32 [k_strip<GaussQ8WideOp<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
+    opn = "GaussQ8Op" if ks <= 11 else "GaussQ8WideOp"
+    run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32 [k_strip<{opn}<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
+    if ks <= 11:
+        I.set_option("gauss.wide_windowed", 1)
+        run(f"GaussianBlur {ks}x{ks} sigma {sg}, 4K BGR u8 x32, windowed wide op [k_strip<GaussQ8WideOp<3,{ks}>>]", lambda: I.gaussian_blur_batch(bgr, out3, (ks, ks), sg, sg), 6 * PX)
+        I.set_option("gauss.wide_windowed", 0)
 I.set_option("gauss.no_wide", 1)
 run("GaussianBlur 11x11 sigma 2, 4K BGR u8 x32, general kernel [k_sepfilter<u8,11>]", lambda: I.gaussian_blur_batch(bgr, out3, (11, 11), 2.0, 2.0), 6 * PX)
 I.set_option("gauss.no_wide", 0)

@@ -200,6 +200,29 @@ def test_gaussian_wide_falls_back_for_tiny_or_two_channel_images(rcv, oracle):
         assert (d.to_numpy() == oracle.gaussian_blur(a, (11, 11), 2.0, 2.0)).all(), shape
 
 
+@pytest.mark.parametrize("cn", [1, 2, 3, 4])
+@pytest.mark.parametrize("ks", [9, 11])
+def test_gaussian_9_and_11_taps_both_strip_ops_agree(rcv, oracle, cn, ks):
+    """9 / 11 taps run the horizontal-first op (GaussQ8Op, 8 warps, 16-row chunks) where the taps stay within the
+    adjacent lanes, the windowed wide op otherwise or on request: both bit-exact, several band heights, ragged strips."""
+    R = rcv
+    for (h, w) in ((203, 517), (16, 16), (130, 1000)):
+        a = oracle.fill_u8(4400 + ks + cn, h * w * cn).reshape((h, w) if cn == 1 else (h, w, cn))
+        want = oracle.gaussian_blur(a, (ks, ks), 1.9, 2.3)
+        s = R.Mat.from_numpy(a).upload()
+        for windowed in (0, 1):
+            for br in (0, 16, 40):
+                R.imgproc.set_option("gauss.wide_windowed", windowed)
+                R.imgproc.set_option("gauss.band_rows", br)
+                try:
+                    d = s.like()
+                    R.imgproc.gaussian_blur(s, d, (ks, ks), 1.9, 2.3)
+                finally:
+                    R.imgproc.set_option("gauss.wide_windowed", 0)
+                    R.imgproc.set_option("gauss.band_rows", 0)
+                assert (d.to_numpy() == want).all(), f"cn{cn} ks{ks} {h}x{w} windowed{windowed} band{br}"
+
+
 @pytest.mark.parametrize("cn", [1, 3])
 @pytest.mark.parametrize("ks", [9, 11, 13, 15])
 def test_f32_wide_strip_kernel(rcv, oracle, cn, ks):
